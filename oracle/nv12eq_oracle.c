@@ -1,0 +1,393 @@
+/*
+ * nv12eq_oracle.c -- CPU restatement of the reference hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the checker, never the product: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The shipped path is the CUDA
+ * library in opencv-opencl_b200/csrc and it has no CPU fallback.
+ *
+ * What it restates
+ * ----------------
+ * The reference (kimkimhun3/OpenCV-OpenCL) does no arithmetic of its own on this path: each
+ * program wraps the first `height` rows of an NV12 buffer as an 8-bit single channel image and
+ * calls OpenCV, then copies (or greys) the chroma plane:
+ *   - NV12 adapter            nextimprovement.cpp:128-165, OpenCVequalHist.cpp:127-142
+ *   - cv::equalizeHist        nextimprovement.cpp:168, OpenCVequalHist.cpp:145, singlecolor.cpp:55
+ *   - cv::CLAHE::apply        clahevideo.cpp:184-195, CLAHECompare.cpp:144-150, clahe1frame.cpp:88-93
+ *   - UV passthrough / 128    nextimprovement.cpp:160 / OpenCVequalHist.cpp:162, clahevideo.cpp:201
+ *   - colour path             singlecolor.cpp:39-66, clahe1frame.cpp:83-102
+ * OpenCV itself is a third-party dependency that is NOT vendored under /root/reference (the
+ * shipped binaries link libopencv_imgproc.so.4.4; compile.sh:10 uses `pkg-config opencv4`, no
+ * version pin).  The algorithm restated here is OpenCV's published one (imgproc histogram.cpp
+ * equalizeHist, imgproc clahe.cpp, imgproc color_yuv 8-bit fixed point), as written down in
+ * SURVEY.md Appendix A.  Parity is PINNED, not assumed: tests/golden/make_golden.py runs the very
+ * functions the reference calls (cv2 4.13.0, same C++ code behind Python bindings) on seeded
+ * inputs and commits digests + small raw fixtures; tests/test_oracle.py checks this file against
+ * them (and against live cv2 whenever cv2 is importable).
+ *
+ * Floating point: every f32 operation below must be a separately rounded IEEE binary32 operation
+ * (OpenCV's x86 baseline build has no FMA).  Build with -ffp-contract=off (see oracle/Makefile).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+enum { UV_COPY = 0, UV_GRAY128 = 1, UV_SKIP = 2 };
+enum { COLOR_YUV = 0, COLOR_YCRCB = 1 };
+
+/* cvRound on x86 = cvtss2si under the default rounding mode = round half to even. */
+static inline int rne(float v) { return (int)lrintf(v); }
+static inline uint8_t sat8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+/* ------------------------------------------------------------------------------------------
+ * Appendix B: deterministic synthetic NV12 frames (all arithmetic mod 2^32).
+ * ---------------------------------------------------------------------------------------- */
+static inline uint32_t fmix32(uint32_t k) {
+    k ^= k >> 16; k *= 0x85EBCA6Bu; k ^= k >> 13; k *= 0xC2B2AE35u; k ^= k >> 16;
+    return k;
+}
+
+ORACLE_API void oracle_synth_y(uint8_t* y, int stride, int W, int H, uint32_t seed, uint32_t frame) {
+    int bw = W / 16 > 1 ? W / 16 : 1;
+    int bh = H / 9 > 1 ? H / 9 : 1;
+    for (int r = 0; r < H; ++r) {
+        for (int c = 0; c < W; ++c) {
+            uint32_t idx = (uint32_t)r * (uint32_t)W + (uint32_t)c;
+            uint32_t k = fmix32(idx * 0x9E3779B1u + seed * 0x85EBCA77u + frame * 0xC2B2AE3Du);
+            int base = 48 + (c * 128) / W + (r * 48) / H;
+            int noise = (int)(k & 63u) - 32;
+            if (((c / bw) + (r / bh)) % 5 == 0) { base = 200; noise = (int)(k & 3u); }
+            y[(size_t)r * stride + c] = sat8(base + noise);
+        }
+    }
+}
+
+ORACLE_API void oracle_synth_uv(uint8_t* uv, int stride, int W, int H, uint32_t seed, uint32_t frame) {
+    int rows = H / 2;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < W; ++c) {
+            uint32_t j = (uint32_t)r * (uint32_t)W + (uint32_t)c;
+            uint32_t k = fmix32(j * 0x9E3779B1u + seed + 0x01234567u + frame * 0xC2B2AE3Du);
+            uv[(size_t)r * stride + c] = (uint8_t)(128 + (int)(k & 31u) - 16);
+        }
+}
+
+/* NV12 frame = H rows of Y then H/2 rows of interleaved UV, all with the same row stride. */
+ORACLE_API void oracle_synth_nv12(uint8_t* nv12, int stride, int W, int H, uint32_t seed, uint32_t frame) {
+    oracle_synth_y(nv12, stride, W, H, seed, frame);
+    oracle_synth_uv(nv12 + (size_t)stride * H, stride, W, H, seed, frame);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A.1 equalizeHist (8UC1).  Follows cv::equalizeHist as called at nextimprovement.cpp:168.
+ * ---------------------------------------------------------------------------------------- */
+ORACLE_API void oracle_hist256(const uint8_t* src, int stride, int W, int H, int32_t hist[256]) {
+    memset(hist, 0, 256 * sizeof(int32_t));
+    for (int r = 0; r < H; ++r) {
+        const uint8_t* p = src + (size_t)r * stride;
+        for (int c = 0; c < W; ++c) hist[p[c]]++;
+    }
+}
+
+/* Returns 1 when the image is constant (lut filled with i0), else 0. */
+ORACLE_API int oracle_equalize_lut(const int32_t hist[256], int64_t total, uint8_t lut[256]) {
+    int i0 = 0;
+    while (i0 < 256 && hist[i0] == 0) ++i0;
+    if (i0 == 256) { memset(lut, 0, 256); return 1; }          /* empty image */
+    if ((int64_t)hist[i0] == total) { memset(lut, i0, 256); return 1; }
+    float scale = 255.0f / (float)(total - hist[i0]);
+    int sum = 0;
+    for (int i = 0; i <= i0; ++i) lut[i] = 0;
+    for (int i = i0 + 1; i < 256; ++i) {
+        sum += hist[i];
+        lut[i] = sat8(rne((float)sum * scale));
+    }
+    return 0;
+}
+
+ORACLE_API void oracle_equalize_hist(const uint8_t* src, int sstride, uint8_t* dst, int dstride, int W, int H) {
+    int32_t hist[256];
+    uint8_t lut[256];
+    if (W <= 0 || H <= 0) return;
+    oracle_hist256(src, sstride, W, H, hist);
+    oracle_equalize_lut(hist, (int64_t)W * H, lut);
+    for (int r = 0; r < H; ++r) {
+        const uint8_t* s = src + (size_t)r * sstride;
+        uint8_t* d = dst + (size_t)r * dstride;
+        for (int c = 0; c < W; ++c) d[c] = lut[s[c]];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A.2 CLAHE (8UC1).  Follows cv::createCLAHE(clip, Size(tx,ty))->apply as called at
+ * clahevideo.cpp:184-195.
+ * ---------------------------------------------------------------------------------------- */
+static inline int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while ((unsigned)p >= (unsigned)len) {
+        if (p < 0) p = -p;
+        else p = 2 * (len - 1) - p;
+    }
+    return p;
+}
+
+/* Geometry shared with the tests: padded size, tile size, integer clip limit. */
+ORACLE_API void oracle_clahe_geometry(int W, int H, double clip, int tx, int ty,
+                                      int* extW, int* extH, int* tw, int* th, int* clipLimit) {
+    int eW = W, eH = H;
+    if (W % tx != 0 || H % ty != 0) {
+        eW = W + (tx - (W % tx));
+        eH = H + (ty - (H % ty));
+    }
+    *extW = eW; *extH = eH;
+    *tw = eW / tx; *th = eH / ty;
+    int area = (*tw) * (*th);
+    int cl = 0;
+    if (clip > 0.0) {
+        cl = (int)(clip * area / 256.0);
+        if (cl < 1) cl = 1;
+    }
+    *clipLimit = cl;
+}
+
+/* luts: tx*ty tables of 256 bytes, row-major over tiles. */
+ORACLE_API void oracle_clahe_tile_luts(const uint8_t* src, int stride, int W, int H, double clip,
+                                       int tx, int ty, uint8_t* luts) {
+    int eW, eH, tw, th, clipLimit;
+    oracle_clahe_geometry(W, H, clip, tx, ty, &eW, &eH, &tw, &th, &clipLimit);
+    float lutScale = 255.0f / (float)(tw * th);
+    for (int tyi = 0; tyi < ty; ++tyi) {
+        for (int txi = 0; txi < tx; ++txi) {
+            int h[256];
+            memset(h, 0, sizeof h);
+            for (int r = tyi * th; r < (tyi + 1) * th; ++r) {
+                const uint8_t* row = src + (size_t)reflect101(r, H) * stride;
+                for (int c = txi * tw; c < (txi + 1) * tw; ++c) h[row[reflect101(c, W)]]++;
+            }
+            if (clipLimit > 0) {
+                int clipped = 0;
+                for (int i = 0; i < 256; ++i)
+                    if (h[i] > clipLimit) { clipped += h[i] - clipLimit; h[i] = clipLimit; }
+                int redistBatch = clipped / 256;
+                int residual = clipped - redistBatch * 256;
+                for (int i = 0; i < 256; ++i) h[i] += redistBatch;
+                if (residual != 0) {
+                    int step = 256 / residual; if (step < 1) step = 1;
+                    for (int i = 0; i < 256 && residual > 0; i += step, residual--) h[i]++;
+                }
+            }
+            uint8_t* lut = luts + (size_t)(tyi * tx + txi) * 256;
+            int sum = 0;
+            for (int i = 0; i < 256; ++i) {
+                sum += h[i];
+                lut[i] = sat8(rne((float)sum * lutScale));
+            }
+        }
+    }
+}
+
+ORACLE_API int oracle_clahe(const uint8_t* src, int sstride, uint8_t* dst, int dstride, int W, int H,
+                            double clip, int tx, int ty) {
+    if (W <= 0 || H <= 0 || tx < 1 || ty < 1) return -1;
+    int eW, eH, tw, th, clipLimit;
+    oracle_clahe_geometry(W, H, clip, tx, ty, &eW, &eH, &tw, &th, &clipLimit);
+    uint8_t* luts = (uint8_t*)malloc((size_t)tx * ty * 256);
+    int* ind1 = (int*)malloc(sizeof(int) * W * 2);
+    float* xa = (float*)malloc(sizeof(float) * W * 2);
+    if (!luts || !ind1 || !xa) { free(luts); free(ind1); free(xa); return -2; }
+    int* ind2 = ind1 + W;
+    float* xa1 = xa + W;
+    oracle_clahe_tile_luts(src, sstride, W, H, clip, tx, ty, luts);
+
+    float inv_tw = 1.0f / (float)tw;
+    float inv_th = 1.0f / (float)th;
+    for (int x = 0; x < W; ++x) {
+        float txf = (float)x * inv_tw - 0.5f;
+        int t1 = (int)floorf(txf);
+        int t2 = t1 + 1;
+        xa[x] = txf - (float)t1;
+        xa1[x] = 1.0f - xa[x];
+        if (t1 < 0) t1 = 0;
+        if (t2 > tx - 1) t2 = tx - 1;
+        ind1[x] = t1; ind2[x] = t2;
+    }
+    for (int y = 0; y < H; ++y) {
+        float tyf = (float)y * inv_th - 0.5f;
+        int t1 = (int)floorf(tyf);
+        int t2 = t1 + 1;
+        float ya = tyf - (float)t1;
+        float ya1 = 1.0f - ya;
+        if (t1 < 0) t1 = 0;
+        if (t2 > ty - 1) t2 = ty - 1;
+        const uint8_t* plane1 = luts + (size_t)t1 * tx * 256;
+        const uint8_t* plane2 = luts + (size_t)t2 * tx * 256;
+        const uint8_t* s = src + (size_t)y * sstride;
+        uint8_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < W; ++x) {
+            int v = s[x];
+            float top = (float)plane1[ind1[x] * 256 + v] * xa1[x] + (float)plane1[ind2[x] * 256 + v] * xa[x];
+            float bot = (float)plane2[ind1[x] * 256 + v] * xa1[x] + (float)plane2[ind2[x] * 256 + v] * xa[x];
+            float res = top * ya1 + bot * ya;
+            d[x] = sat8(rne(res));
+        }
+    }
+    free(luts); free(ind1); free(xa);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * NV12 frame-in / frame-out forms (the per-frame body of the reference worker,
+ * nextimprovement.cpp:128-170 and clahevideo.cpp:158-201).
+ * ---------------------------------------------------------------------------------------- */
+static void uv_plane(const uint8_t* in, uint8_t* out, int W, int H, int stride, int uv_mode) {
+    size_t off = (size_t)stride * H;
+    int rows = H / 2;
+    if (uv_mode == UV_SKIP) return;
+    for (int r = 0; r < rows; ++r) {
+        if (uv_mode == UV_COPY) {
+            if (out != in) memcpy(out + off + (size_t)r * stride, in + off + (size_t)r * stride, (size_t)W);
+        } else {
+            memset(out + off + (size_t)r * stride, 128, (size_t)W);
+        }
+    }
+}
+
+ORACLE_API int oracle_nv12_equalize_hist(const uint8_t* in, uint8_t* out, int W, int H, int stride, int uv_mode) {
+    if (!in || !out || W <= 0 || H <= 0 || stride < W) return -1;
+    uv_plane(in, out, W, H, stride, uv_mode);
+    oracle_equalize_hist(in, stride, out, stride, W, H);
+    return 0;
+}
+
+ORACLE_API int oracle_nv12_clahe(const uint8_t* in, uint8_t* out, int W, int H, int stride,
+                                 double clip, int tx, int ty, int uv_mode) {
+    if (!in || !out || W <= 0 || H <= 0 || stride < W) return -1;
+    uv_plane(in, out, W, H, stride, uv_mode);
+    return oracle_clahe(in, stride, out, stride, W, H, clip, tx, ty);
+}
+
+/* Frame-parallel batch forms: one frame per OpenMP thread, mirroring the reference's
+ * --workers N frame-level data parallelism (OpenCVequalHist.cpp:397-402). */
+ORACLE_API int oracle_nv12_equalize_hist_batch(const uint8_t* in, uint8_t* out, int n, size_t pitch,
+                                               int W, int H, int stride, int uv_mode, int threads) {
+    int rc = 0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int i = 0; i < n; ++i) {
+        int r = oracle_nv12_equalize_hist(in + (size_t)i * pitch, out + (size_t)i * pitch, W, H, stride, uv_mode);
+        if (r) rc = r;
+    }
+    return rc;
+}
+
+ORACLE_API int oracle_nv12_clahe_batch(const uint8_t* in, uint8_t* out, int n, size_t pitch, int W, int H,
+                                       int stride, double clip, int tx, int ty, int uv_mode, int threads) {
+    int rc = 0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int i = 0; i < n; ++i) {
+        int r = oracle_nv12_clahe(in + (size_t)i * pitch, out + (size_t)i * pitch, W, H, stride, clip, tx, ty, uv_mode);
+        if (r) rc = r;
+    }
+    return rc;
+}
+
+ORACLE_API int oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A.3 8-bit colour conversions (Q14), and the colour path of singlecolor.cpp:39-66:
+ * BGR -> YUV (or YCrCb), equalize channel 0, -> BGR.
+ * ---------------------------------------------------------------------------------------- */
+static inline int descale14(int v) { return (v + 8192) >> 14; }
+
+static inline void bgr_to_ycc(int B, int G, int R, int mode, uint8_t* o0, uint8_t* o1, uint8_t* o2) {
+    int Y = descale14(1868 * B + 9617 * G + 4899 * R);
+    if (mode == COLOR_YUV) {
+        int U = descale14((B - Y) * 8061 + (128 << 14));
+        int V = descale14((R - Y) * 14369 + (128 << 14));
+        *o0 = sat8(Y); *o1 = sat8(U); *o2 = sat8(V);
+    } else {
+        int Cr = descale14((R - Y) * 11682 + (128 << 14));
+        int Cb = descale14((B - Y) * 9241 + (128 << 14));
+        *o0 = sat8(Y); *o1 = sat8(Cr); *o2 = sat8(Cb);
+    }
+}
+
+static inline void ycc_to_bgr(int c0, int c1, int c2, int mode, uint8_t* B, uint8_t* G, uint8_t* R) {
+    if (mode == COLOR_YUV) {
+        int U = c1 - 128, V = c2 - 128;
+        *B = sat8(c0 + descale14(U * 33292));
+        *G = sat8(c0 + descale14(U * -6472 + V * -9519));
+        *R = sat8(c0 + descale14(V * 18678));
+    } else {
+        int Cr = c1 - 128, Cb = c2 - 128;
+        *B = sat8(c0 + descale14(Cb * 29049));
+        *G = sat8(c0 + descale14(Cb * -5636 + Cr * -11698));
+        *R = sat8(c0 + descale14(Cr * 22987));
+    }
+}
+
+ORACLE_API void oracle_bgr2ycc(const uint8_t* bgr, int sstride, uint8_t* ycc, int dstride, int W, int H, int mode) {
+    for (int r = 0; r < H; ++r) {
+        const uint8_t* s = bgr + (size_t)r * sstride;
+        uint8_t* d = ycc + (size_t)r * dstride;
+        for (int c = 0; c < W; ++c) bgr_to_ycc(s[3 * c], s[3 * c + 1], s[3 * c + 2], mode, d + 3 * c, d + 3 * c + 1, d + 3 * c + 2);
+    }
+}
+
+ORACLE_API void oracle_ycc2bgr(const uint8_t* ycc, int sstride, uint8_t* bgr, int dstride, int W, int H, int mode) {
+    for (int r = 0; r < H; ++r) {
+        const uint8_t* s = ycc + (size_t)r * sstride;
+        uint8_t* d = bgr + (size_t)r * dstride;
+        for (int c = 0; c < W; ++c) ycc_to_bgr(s[3 * c], s[3 * c + 1], s[3 * c + 2], mode, d + 3 * c, d + 3 * c + 1, d + 3 * c + 2);
+    }
+}
+
+/* use_clahe == 0: equalizeHist on channel 0 (singlecolor.cpp:55); else CLAHE (clahe1frame.cpp:93). */
+ORACLE_API int oracle_color_equalize(const uint8_t* bgr_in, uint8_t* bgr_out, int W, int H, int stride, int mode,
+                                     int use_clahe, double clip, int tx, int ty) {
+    if (!bgr_in || !bgr_out || W <= 0 || H <= 0 || stride < 3 * W) return -1;
+    size_t n = (size_t)W * H;
+    uint8_t* ycc = (uint8_t*)malloc(n * 3);
+    uint8_t* y = (uint8_t*)malloc(n * 2);
+    if (!ycc || !y) { free(ycc); free(y); return -2; }
+    uint8_t* y2 = y + n;
+    oracle_bgr2ycc(bgr_in, stride, ycc, 3 * W, W, H, mode);
+    for (size_t i = 0; i < n; ++i) y[i] = ycc[3 * i];
+    int rc = 0;
+    if (use_clahe) rc = oracle_clahe(y, W, y2, W, W, H, clip, tx, ty);
+    else oracle_equalize_hist(y, W, y2, W, W, H);
+    for (size_t i = 0; i < n; ++i) ycc[3 * i] = y2[i];
+    oracle_ycc2bgr(ycc, 3 * W, bgr_out, stride, W, H, mode);
+    free(ycc); free(y);
+    return rc;
+}
+
+/* Colour-path synthetic input (Appendix B): B,G,R planes = Y syntheses with seeds 3026/4026/5026. */
+ORACLE_API void oracle_synth_bgr(uint8_t* bgr, int stride, int W, int H, uint32_t frame) {
+    uint8_t* plane = (uint8_t*)malloc((size_t)W * H);
+    if (!plane) return;
+    const uint32_t seeds[3] = {3026u, 4026u, 5026u};
+    for (int ch = 0; ch < 3; ++ch) {
+        oracle_synth_y(plane, W, W, H, seeds[ch], frame);
+        for (int r = 0; r < H; ++r)
+            for (int c = 0; c < W; ++c) bgr[(size_t)r * stride + 3 * c + ch] = plane[(size_t)r * W + c];
+    }
+    free(plane);
+}
