@@ -1,0 +1,179 @@
+/*
+ * nv12eq.h -- C-ABI of libnv12eq.so: B200-native (sm_100a CUDA) histogram equalization and CLAHE on the
+ * Y plane of NV12 frames, UV passed through.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Every entry point replaces one piece of the reference's per-frame hot path (citations are into the
+ * reference tree kimkimhun3/OpenCV-OpenCL):
+ *
+ *   nv12eq_create / nv12eq_destroy      <- shared + per-worker device context set-up,
+ *                                          OpenCLequalHist.cpp:106-161 (SharedOpenCLContext/WorkerOpenCLContext :63-81),
+ *                                          buffers cached by size like allocate_worker_opencl_buffers :175-192
+ *   nv12eq_equalize_hist                <- the frame body of the worker: UV memcpy + cv::equalizeHist on views,
+ *                                          nextimprovement.cpp:128-170 (also OpenCVequalHist.cpp:127-163,
+ *                                          ColoropenCVCwqualHist.cpp:146-165) and the device launch protocol it
+ *                                          replaces, OpenCLequalHist.cpp:349-365 + NV12 rebuild :388-390
+ *   nv12eq_clahe                        <- cv::createCLAHE(clip, Size(t,t)) + clahe->apply on the Y view + NV12
+ *                                          rebuild, clahevideo.cpp:178-201,:497 (CLAHECompare.cpp:144-154)
+ *   nv12eq_*_batch / submit / wait      <- N worker threads popping one queue, OpenCVequalHist.cpp:71-98,397-402
+ *   nv12eq_*_device                     <- the kernel boundary equalizeHist_accel(in, ref, out, rows, cols),
+ *                                          accel.cpp:36-61 (device buffers in, device buffers out)
+ *   nv12eq_color_equalize / _clahe      <- cvtColor(BGR2YUV) -> split -> equalizeHist/CLAHE(Y) -> merge ->
+ *                                          cvtColor(YUV2BGR), singlecolor.cpp:39-66, clahe1frame.cpp:83-102
+ *   nv12eq_get_counters                 <- the Counters struct + status tick, OpenCLequalHist.cpp:45-61,439-508
+ *
+ * Conventions:
+ *   - every function returns an nv12eq_status (0 = ok); nothing throws, aborts or exits.  A failed frame is
+ *     the caller's to drop, as the reference does (processing_errors / opencl_errors, OpenCLequalHist.cpp:339-344).
+ *   - the caller owns both frame buffers for the duration of the call; the library owns only device memory and
+ *     pinned staging memory.  Output must not partially overlap input; in == out (in place) is allowed.
+ *   - one context per calling thread (thread-compatible, like one WorkerOpenCLContext per worker); contexts on
+ *     the same device share the device's primary CUDA context.
+ *   - NV12 layout: `height` rows of Y then `height/2` rows of interleaved UV, every row `stride` bytes apart,
+ *     `stride >= width`; a frame occupies stride*(height + height/2) bytes.  Bytes between width and stride are
+ *     never read or written.  The reference assumes stride == width (OpenCVequalHist.cpp:140).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ *     NV12EQ_ERR_NO_DEVICE / NV12EQ_ERR_CUDA.
+ */
+#ifndef NV12EQ_H_
+#define NV12EQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define NV12EQ_VERSION_MAJOR 0
+#define NV12EQ_VERSION_MINOR 1
+
+typedef struct nv12eq_ctx nv12eq_ctx;
+
+typedef enum nv12eq_status {
+    NV12EQ_OK = 0,
+    NV12EQ_ERR_INVALID_ARGUMENT = 1, /* null pointer, non-positive size, stride < width, bad enum, bad tile grid */
+    NV12EQ_ERR_SHORT_BUFFER = 2,     /* buffer smaller than stride*(h + h/2): reference rejects these too
+                                        (OpenCVequalHist.cpp:132-137) */
+    NV12EQ_ERR_CUDA = 3,             /* a CUDA call failed; see nv12eq_last_error_string */
+    NV12EQ_ERR_NO_DEVICE = 4,        /* no CUDA device / wrong architecture (needs sm_100) */
+    NV12EQ_ERR_OUT_OF_MEMORY = 5,
+    NV12EQ_ERR_BAD_SLOT = 6,         /* slot index out of range, or slot busy / not submitted */
+    NV12EQ_ERR_TOO_LARGE = 7         /* frame exceeds the max_width/max_height given to nv12eq_create, or 2^31 pixels */
+} nv12eq_status;
+
+/* What to put in the output chroma plane. */
+typedef enum nv12eq_uv_mode {
+    NV12EQ_UV_COPY = 0,    /* passthrough (nextimprovement.cpp:160, ColoropenCVCwqualHist.cpp:165) -- the default */
+    NV12EQ_UV_GRAY128 = 1, /* neutral grey (OpenCVequalHist.cpp:162, clahevideo.cpp:201) */
+    NV12EQ_UV_SKIP = 2     /* leave the output chroma bytes untouched (Y-only callers) */
+} nv12eq_uv_mode;
+
+typedef enum nv12eq_color_mode {
+    NV12EQ_COLOR_YUV = 0,  /* COLOR_BGR2YUV / COLOR_YUV2BGR, what the reference uses (singlecolor.cpp:39,66) */
+    NV12EQ_COLOR_YCRCB = 1 /* COLOR_BGR2YCrCb / COLOR_YCrCb2BGR (BASELINE.json config 5 wording) */
+} nv12eq_color_mode;
+
+/* Cumulative per-context counters (the reference's Counters struct, OpenCLequalHist.cpp:45-61). */
+typedef struct nv12eq_counters {
+    uint64_t frames;        /* frames processed successfully */
+    uint64_t bytes_in;      /* host->device bytes moved by host-buffer entry points */
+    uint64_t bytes_out;     /* device->host bytes */
+    uint64_t errors;        /* calls that returned non-zero */
+    uint64_t kernel_launches; /* CUDA kernels launched by this context */
+    uint64_t busy_us;       /* wall time spent inside synchronous entry points */
+} nv12eq_counters;
+
+/* ---- library / context -------------------------------------------------------------------------------- */
+int nv12eq_version(void);                       /* major*100 + minor */
+const char* nv12eq_status_string(int status);
+/* Last error text of this context (or of the calling thread's last failed nv12eq_create when ctx == NULL). */
+const char* nv12eq_last_error_string(const nv12eq_ctx* ctx);
+
+/* device: CUDA ordinal.  max_width/max_height: largest frame this context will see (sizes staging memory).
+ * slots: number of host batches that may be in flight through nv12eq_submit_* (>= 1; 2 = double buffering).
+ * Device and pinned memory are allocated lazily and cached by size. */
+int nv12eq_create(int device, int max_width, int max_height, int slots, nv12eq_ctx** out_ctx);
+void nv12eq_destroy(nv12eq_ctx* ctx);
+int nv12eq_get_counters(const nv12eq_ctx* ctx, nv12eq_counters* out);
+/* Tuning knobs (0 keeps the built-in default): chunks per frame, frame lag of the fused kernel, CTAs per SM,
+ * fused (1) vs two-kernel (2) schedule. */
+int nv12eq_set_tuning(nv12eq_ctx* ctx, int chunks_per_frame, int lag_frames, int ctas_per_sm, int schedule);
+
+/* Pinned host memory helpers: buffers from here skip the staging copy inside the host entry points. */
+int nv12eq_host_alloc(size_t bytes, void** out_ptr);
+int nv12eq_host_free(void* ptr);
+
+/* ---- host frame in / frame out (synchronous) ---------------------------------------------------------- */
+int nv12eq_equalize_hist(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, uint8_t* out, size_t out_size,
+                         int width, int height, int stride, int uv_mode);
+/* clip_limit <= 0 disables clipping (as in OpenCV).  tiles_x/tiles_y >= 1 (reference: --tile, default 8). */
+int nv12eq_clahe(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, uint8_t* out, size_t out_size, int width,
+                 int height, int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode);
+
+/* ---- host batches: n_frames frames, frame k at in + k*frame_pitch (frame_pitch >= stride*(h+h/2)) ------ */
+/* Synchronous; internally pipelined (pinned double buffering, H2D / kernels / D2H on separate streams). */
+int nv12eq_equalize_hist_batch(nv12eq_ctx* ctx, const uint8_t* in, uint8_t* out, int n_frames, size_t frame_pitch,
+                               int width, int height, int stride, int uv_mode);
+int nv12eq_clahe_batch(nv12eq_ctx* ctx, const uint8_t* in, uint8_t* out, int n_frames, size_t frame_pitch,
+                       int width, int height, int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode);
+/* Asynchronous: returns once the work is queued on slot `slot`; buffers stay owned by the caller but must not be
+ * touched until nv12eq_wait(ctx, slot) returns.  nv12eq_query returns NV12EQ_OK when done, NV12EQ_ERR_BAD_SLOT
+ * while still running. */
+int nv12eq_submit_equalize_hist(nv12eq_ctx* ctx, int slot, const uint8_t* in, uint8_t* out, int n_frames,
+                                size_t frame_pitch, int width, int height, int stride, int uv_mode);
+int nv12eq_submit_clahe(nv12eq_ctx* ctx, int slot, const uint8_t* in, uint8_t* out, int n_frames, size_t frame_pitch,
+                        int width, int height, int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode);
+int nv12eq_wait(nv12eq_ctx* ctx, int slot);
+int nv12eq_query(nv12eq_ctx* ctx, int slot);
+
+/* ---- device-resident forms (d_* are device pointers; asynchronous on `cuda_stream`) -------------------- */
+/* cuda_stream is a cudaStream_t passed as void* (NULL = the context's own stream; then nv12eq_sync waits). */
+int nv12eq_equalize_hist_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t frame_pitch,
+                                int width, int height, int stride, int uv_mode, void* cuda_stream);
+int nv12eq_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t frame_pitch,
+                        int width, int height, int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode,
+                        void* cuda_stream);
+int nv12eq_sync(nv12eq_ctx* ctx);
+
+/* Stage-level device forms for the spatially split single-frame mode: a rank histograms
+ * its band of rows, the 256-bin histograms are summed across ranks by the caller (ncclAllReduce), and every rank
+ * applies the LUT of the summed histogram to its band.
+ *   nv12eq_hist_device:   d_hist[n_planes][256] (uint32) += histogram of plane k (height rows of `width` bytes)
+ *   nv12eq_equalize_apply_device: out plane = LUT(d_hist[k], total_pixels)[in plane]; total_pixels is the pixel
+ *                                 count of the WHOLE frame the summed histogram describes. */
+int nv12eq_hist_device(nv12eq_ctx* ctx, const uint8_t* d_y, int n_planes, size_t plane_pitch, int width, int height,
+                       int stride, uint32_t* d_hist, void* cuda_stream);
+int nv12eq_equalize_apply_device(nv12eq_ctx* ctx, const uint8_t* d_y_in, uint8_t* d_y_out, int n_planes,
+                                 size_t plane_pitch, int width, int height, int stride, const uint32_t* d_hist,
+                                 int64_t total_pixels, void* cuda_stream);
+
+/* ---- colour path: packed 8-bit BGR in, BGR out (stride in bytes, >= 3*width) --------------------------- */
+int nv12eq_color_equalize(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_out, int width, int height, int stride,
+                          int color_mode);
+int nv12eq_color_clahe(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_out, int width, int height, int stride,
+                       int color_mode, double clip_limit, int tiles_x, int tiles_y);
+int nv12eq_color_equalize_device(nv12eq_ctx* ctx, const uint8_t* d_bgr_in, uint8_t* d_bgr_out, int n_frames,
+                                 size_t frame_pitch, int width, int height, int stride, int color_mode,
+                                 void* cuda_stream);
+int nv12eq_color_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_bgr_in, uint8_t* d_bgr_out, int n_frames,
+                              size_t frame_pitch, int width, int height, int stride, int color_mode, double clip_limit,
+                              int tiles_x, int tiles_y, void* cuda_stream);
+
+/* ---- synthetic inputs on the device (SURVEY.md Appendix B generator; bench/test utility) --------------- */
+/* Frame k of the batch is synth_nv12(width, height, seed, first_frame + k). */
+int nv12eq_synth_nv12_device(nv12eq_ctx* ctx, uint8_t* d_out, int n_frames, size_t frame_pitch, int width, int height,
+                             int stride, uint32_t seed, uint32_t first_frame, void* cuda_stream);
+/* BGR frame k = planes synthesised with seeds 3026/4026/5026 and frame first_frame + k. */
+int nv12eq_synth_bgr_device(nv12eq_ctx* ctx, uint8_t* d_out, int n_frames, size_t frame_pitch, int width, int height,
+                            int stride, uint32_t first_frame, void* cuda_stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* NV12EQ_H_ */

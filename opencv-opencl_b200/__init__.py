@@ -1,0 +1,419 @@
+"""nv12eq -- B200-native NV12 histogram equalization / CLAHE (host-side Python mirror of the reference call shape).
+
+The reference (kimkimhun3/OpenCV-OpenCL) has no plugin registry; its operator interface for this path is the per-frame
+body of the worker (nextimprovement.cpp:128-170, clahevideo.cpp:178-201): an NV12 buffer plus width/height goes in,
+an NV12 buffer comes out, with ``cv::equalizeHist`` or ``cv::createCLAHE(clipLimit, Size(t, t))->apply`` run on the
+Y view and the chroma plane copied or greyed.  This module keeps those names and argument meanings
+(``equalizeHist``, ``createCLAHE(clipLimit=, tileGridSize=)``, ``.apply``, ``setClipLimit``, ``setTilesGridSize``)
+over the C-ABI of ``libnv12eq.so`` (``include/nv12eq.h``).  Everything here is a thin ctypes layer: all arithmetic
+runs in the hand-written sm_100a CUDA kernels under ``csrc/``.  There is no CPU fallback -- if the shared library is
+missing, or no B200 is visible, calls raise.
+
+Import note: the directory name contains a hyphen, so use ``importlib.import_module("opencv-opencl_b200")`` or the
+``opencv_opencl_b200`` shim module at the repo root.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnv12eq.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nv12eq.h")
+
+# enums of include/nv12eq.h
+OK, ERR_INVALID_ARGUMENT, ERR_SHORT_BUFFER, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_BAD_SLOT, ERR_TOO_LARGE = range(8)
+UV_COPY, UV_GRAY128, UV_SKIP = 0, 1, 2
+COLOR_YUV, COLOR_YCRCB = 0, 1
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_c_int, _c_sz, _c_dbl, _c_vp, _c_u32 = ctypes.c_int, ctypes.c_size_t, ctypes.c_double, ctypes.c_void_p, ctypes.c_uint32
+
+
+class Nv12eqError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"nv12eq status {status}: {message}")
+        self.status = status
+
+
+class Counters(ctypes.Structure):
+    _fields_ = [("frames", ctypes.c_uint64), ("bytes_in", ctypes.c_uint64), ("bytes_out", ctypes.c_uint64),
+                ("errors", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("busy_us", ctypes.c_uint64)]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ into libnv12eq.so for sm_100a with nvcc (in-tree, so the .so travels with the repo)."""
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))] + [HEADER_PATH]
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        out = subprocess.run(["make", "-C", csrc] + (["-B"] if force else []), capture_output=True, text=True)
+        if verbose or out.returncode:
+            print(out.stdout + out.stderr)
+        if out.returncode:
+            raise RuntimeError("building libnv12eq.so failed (see output above)")
+    return LIB_PATH
+
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "nv12eq_version": (_c_int, []),
+    "nv12eq_status_string": (ctypes.c_char_p, [_c_int]),
+    "nv12eq_last_error_string": (ctypes.c_char_p, [_c_vp]),
+    "nv12eq_create": (_c_int, [_c_int, _c_int, _c_int, _c_int, ctypes.POINTER(_c_vp)]),
+    "nv12eq_destroy": (None, [_c_vp]),
+    "nv12eq_get_counters": (_c_int, [_c_vp, ctypes.POINTER(Counters)]),
+    "nv12eq_set_tuning": (_c_int, [_c_vp, _c_int, _c_int, _c_int, _c_int]),
+    "nv12eq_host_alloc": (_c_int, [_c_sz, ctypes.POINTER(_c_vp)]),
+    "nv12eq_host_free": (_c_int, [_c_vp]),
+    "nv12eq_equalize_hist": (_c_int, [_c_vp, _c_vp, _c_sz, _c_vp, _c_sz, _c_int, _c_int, _c_int, _c_int]),
+    "nv12eq_clahe": (_c_int, [_c_vp, _c_vp, _c_sz, _c_vp, _c_sz, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_int]),
+    "nv12eq_equalize_hist_batch": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int]),
+    "nv12eq_clahe_batch": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_int]),
+    "nv12eq_submit_equalize_hist": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int]),
+    "nv12eq_submit_clahe": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_int]),
+    "nv12eq_wait": (_c_int, [_c_vp, _c_int]),
+    "nv12eq_query": (_c_int, [_c_vp, _c_int]),
+    "nv12eq_equalize_hist_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "nv12eq_clahe_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_int, _c_vp]),
+    "nv12eq_sync": (_c_int, [_c_vp]),
+    "nv12eq_hist_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "nv12eq_equalize_apply_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_vp, ctypes.c_int64, _c_vp]),
+    "nv12eq_color_equalize": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int]),
+    "nv12eq_color_clahe": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int]),
+    "nv12eq_color_equalize_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "nv12eq_color_clahe_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_vp]),
+    "nv12eq_synth_nv12_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_u32, _c_u32, _c_vp]),
+    "nv12eq_synth_bgr_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_u32, _c_vp]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen libnv12eq.so and bind every symbol include/nv12eq.h declares.  Raises if the library is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() / make -C "
+                              f"{os.path.join(_HERE, 'csrc')}.  nv12eq has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here == header and library out of sync
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def nv12_frame_bytes(width: int, height: int, stride: Optional[int] = None) -> int:
+    stride = width if stride is None else stride
+    return stride * (height + height // 2)
+
+
+def _ptr(buf) -> int:
+    """Address of a NumPy array, torch tensor (host or device), ctypes buffer or raw integer."""
+    if buf is None:
+        return 0
+    if isinstance(buf, int):
+        return buf
+    if isinstance(buf, np.ndarray):
+        return buf.ctypes.data
+    if hasattr(buf, "data_ptr"):
+        return int(buf.data_ptr())
+    return ctypes.addressof(buf)
+
+
+def _nbytes(buf) -> int:
+    if isinstance(buf, np.ndarray):
+        return buf.nbytes
+    if hasattr(buf, "numel"):
+        return int(buf.numel() * buf.element_size())
+    return ctypes.sizeof(buf)
+
+
+def _stream_ptr(stream) -> int:
+    if stream is None:
+        return 0
+    if isinstance(stream, int):
+        return stream
+    return int(stream.cuda_stream)  # torch.cuda.Stream
+
+
+class PinnedBuffer:
+    """Page-locked host memory from nv12eq_host_alloc, viewed as a uint8 NumPy array (``.array``)."""
+
+    def __init__(self, nbytes: int):
+        self._lib = load_library()
+        p = _c_vp()
+        st = self._lib.nv12eq_host_alloc(nbytes, ctypes.byref(p))
+        if st != OK:
+            raise Nv12eqError(st, f"nv12eq_host_alloc({nbytes}) failed")
+        self.ptr = p.value
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.nv12eq_host_free(self.ptr)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One device context (the reference's per-worker OpenCL context, OpenCLequalHist.cpp:71-81,142-161).
+
+    Thread-compatible: use one Context per calling thread.
+    """
+
+    def __init__(self, device: int = 0, max_width: int = 4096, max_height: int = 2304, slots: int = 2):
+        self._lib = load_library()
+        h = _c_vp()
+        st = self._lib.nv12eq_create(device, max_width, max_height, slots, ctypes.byref(h))
+        if st != OK:
+            msg = self._lib.nv12eq_last_error_string(None).decode()
+            raise Nv12eqError(st, msg or self._lib.nv12eq_status_string(st).decode())
+        self._h = h
+        self.device = device
+        self.slots = slots
+
+    # -- plumbing ---------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nv12eq_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != OK:
+            raise Nv12eqError(st, self._lib.nv12eq_last_error_string(self._h).decode()
+                              or self._lib.nv12eq_status_string(st).decode())
+
+    def status(self, st: int) -> str:
+        return self._lib.nv12eq_status_string(st).decode()
+
+    def last_error(self) -> str:
+        return self._lib.nv12eq_last_error_string(self._h).decode()
+
+    def counters(self) -> dict:
+        c = Counters()
+        self._check(self._lib.nv12eq_get_counters(self._h, ctypes.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in Counters._fields_}
+
+    def set_tuning(self, chunks_per_frame: int = 0, lag_frames: int = 0, ctas_per_sm: int = 0, schedule: int = 0):
+        self._check(self._lib.nv12eq_set_tuning(self._h, chunks_per_frame, lag_frames, ctas_per_sm, schedule))
+
+    def sync(self):
+        self._check(self._lib.nv12eq_sync(self._h))
+
+    # -- host frame in / frame out ----------------------------------------------------------------------
+    def equalize_hist(self, nv12, width: int, height: int, stride: Optional[int] = None, uv_mode: int = UV_COPY,
+                      out=None, raw_status: bool = False):
+        """nextimprovement.cpp:159-168: out = NV12 frame with equalizeHist(Y) and the chroma plane per uv_mode."""
+        stride = width if stride is None else stride
+        out = np.empty_like(nv12) if out is None else out
+        st = self._lib.nv12eq_equalize_hist(self._h, _ptr(nv12), _nbytes(nv12), _ptr(out), _nbytes(out), width, height,
+                                            stride, uv_mode)
+        if raw_status:
+            return st
+        self._check(st)
+        return out
+
+    def clahe(self, nv12, width: int, height: int, clip_limit: float = 2.0, tiles: Tuple[int, int] = (8, 8),
+              stride: Optional[int] = None, uv_mode: int = UV_COPY, out=None, raw_status: bool = False):
+        """clahevideo.cpp:178-201: out = NV12 frame with CLAHE(Y); tiles = (tilesX, tilesY) as in cv::Size."""
+        stride = width if stride is None else stride
+        out = np.empty_like(nv12) if out is None else out
+        st = self._lib.nv12eq_clahe(self._h, _ptr(nv12), _nbytes(nv12), _ptr(out), _nbytes(out), width, height, stride,
+                                    float(clip_limit), int(tiles[0]), int(tiles[1]), uv_mode)
+        if raw_status:
+            return st
+        self._check(st)
+        return out
+
+    def equalize_hist_batch(self, frames, width, height, stride=None, uv_mode=UV_COPY, out=None, n_frames=None,
+                            frame_pitch=None):
+        stride = width if stride is None else stride
+        n, pitch = self._batch_shape(frames, n_frames, frame_pitch)
+        out = np.empty_like(frames) if out is None else out
+        self._check(self._lib.nv12eq_equalize_hist_batch(self._h, _ptr(frames), _ptr(out), n, pitch, width, height, stride,
+                                                         uv_mode))
+        return out
+
+    def clahe_batch(self, frames, width, height, clip_limit=2.0, tiles=(8, 8), stride=None, uv_mode=UV_COPY, out=None,
+                    n_frames=None, frame_pitch=None):
+        stride = width if stride is None else stride
+        n, pitch = self._batch_shape(frames, n_frames, frame_pitch)
+        out = np.empty_like(frames) if out is None else out
+        self._check(self._lib.nv12eq_clahe_batch(self._h, _ptr(frames), _ptr(out), n, pitch, width, height, stride,
+                                                 float(clip_limit), int(tiles[0]), int(tiles[1]), uv_mode))
+        return out
+
+    @staticmethod
+    def _batch_shape(frames, n_frames, frame_pitch):
+        if n_frames is not None:
+            return int(n_frames), int(frame_pitch)
+        assert frames.ndim == 2, "batch must be (n_frames, frame_bytes)"
+        return int(frames.shape[0]), int(frames.shape[1] * frames.itemsize if isinstance(frames, np.ndarray)
+                                         else frames.stride(0) * frames.element_size())
+
+    # -- asynchronous slots -----------------------------------------------------------------------------
+    def submit_equalize_hist(self, slot, frames, out, n_frames, frame_pitch, width, height, stride=None, uv_mode=UV_COPY):
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_submit_equalize_hist(self._h, slot, _ptr(frames), _ptr(out), n_frames, frame_pitch,
+                                                          width, height, stride, uv_mode))
+
+    def submit_clahe(self, slot, frames, out, n_frames, frame_pitch, width, height, clip_limit=2.0, tiles=(8, 8),
+                     stride=None, uv_mode=UV_COPY):
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_submit_clahe(self._h, slot, _ptr(frames), _ptr(out), n_frames, frame_pitch, width,
+                                                  height, stride, float(clip_limit), int(tiles[0]), int(tiles[1]), uv_mode))
+
+    def wait(self, slot: int):
+        self._check(self._lib.nv12eq_wait(self._h, slot))
+
+    def query(self, slot: int) -> bool:
+        st = self._lib.nv12eq_query(self._h, slot)
+        if st == OK:
+            return True
+        if st == ERR_BAD_SLOT:
+            return False
+        self._check(st)
+        return False
+
+    # -- device-resident forms (torch tensors or raw device addresses) -----------------------------------
+    def equalize_hist_device(self, d_in, d_out, n_frames, frame_pitch, width, height, stride=None, uv_mode=UV_COPY,
+                             stream=None):
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_equalize_hist_device(self._h, _ptr(d_in), _ptr(d_out), n_frames, frame_pitch, width,
+                                                          height, stride, uv_mode, _stream_ptr(stream)))
+
+    def clahe_device(self, d_in, d_out, n_frames, frame_pitch, width, height, clip_limit=2.0, tiles=(8, 8), stride=None,
+                     uv_mode=UV_COPY, stream=None):
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_clahe_device(self._h, _ptr(d_in), _ptr(d_out), n_frames, frame_pitch, width, height,
+                                                  stride, float(clip_limit), int(tiles[0]), int(tiles[1]), uv_mode,
+                                                  _stream_ptr(stream)))
+
+    def hist_device(self, d_y, n_planes, plane_pitch, width, height, d_hist, stride=None, stream=None):
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_hist_device(self._h, _ptr(d_y), n_planes, plane_pitch, width, height, stride,
+                                                 _ptr(d_hist), _stream_ptr(stream)))
+
+    def equalize_apply_device(self, d_y_in, d_y_out, n_planes, plane_pitch, width, height, d_hist, total_pixels,
+                              stride=None, stream=None):
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_equalize_apply_device(self._h, _ptr(d_y_in), _ptr(d_y_out), n_planes, plane_pitch,
+                                                           width, height, stride, _ptr(d_hist), int(total_pixels),
+                                                           _stream_ptr(stream)))
+
+    # -- colour path ------------------------------------------------------------------------------------
+    def color_equalize(self, bgr: np.ndarray, color_mode: int = COLOR_YUV, out=None) -> np.ndarray:
+        """singlecolor.cpp:39-66 on a (H, W, 3) uint8 BGR image."""
+        h, w, _ = bgr.shape
+        out = np.empty_like(bgr) if out is None else out
+        self._check(self._lib.nv12eq_color_equalize(self._h, _ptr(bgr), _ptr(out), w, h, bgr.strides[0], color_mode))
+        return out
+
+    def color_clahe(self, bgr: np.ndarray, clip_limit=3.0, tiles=(4, 4), color_mode: int = COLOR_YUV, out=None):
+        """clahe1frame.cpp:83-102 (defaults clip 3.0, tile 4: clahe1frame.cpp:55-56)."""
+        h, w, _ = bgr.shape
+        out = np.empty_like(bgr) if out is None else out
+        self._check(self._lib.nv12eq_color_clahe(self._h, _ptr(bgr), _ptr(out), w, h, bgr.strides[0], color_mode,
+                                                 float(clip_limit), int(tiles[0]), int(tiles[1])))
+        return out
+
+    def color_equalize_device(self, d_in, d_out, n_frames, frame_pitch, width, height, stride=None, color_mode=COLOR_YUV,
+                              stream=None):
+        stride = 3 * width if stride is None else stride
+        self._check(self._lib.nv12eq_color_equalize_device(self._h, _ptr(d_in), _ptr(d_out), n_frames, frame_pitch, width,
+                                                           height, stride, color_mode, _stream_ptr(stream)))
+
+    def color_clahe_device(self, d_in, d_out, n_frames, frame_pitch, width, height, clip_limit=3.0, tiles=(4, 4),
+                           stride=None, color_mode=COLOR_YUV, stream=None):
+        stride = 3 * width if stride is None else stride
+        self._check(self._lib.nv12eq_color_clahe_device(self._h, _ptr(d_in), _ptr(d_out), n_frames, frame_pitch, width,
+                                                        height, stride, color_mode, float(clip_limit), int(tiles[0]),
+                                                        int(tiles[1]), _stream_ptr(stream)))
+
+    # -- synthetic inputs -------------------------------------------------------------------------------
+    def synth_nv12_device(self, d_out, n_frames, frame_pitch, width, height, stride=None, seed=2026, first_frame=0,
+                          stream=None):
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_synth_nv12_device(self._h, _ptr(d_out), n_frames, frame_pitch, width, height, stride,
+                                                       seed, first_frame, _stream_ptr(stream)))
+
+    def synth_bgr_device(self, d_out, n_frames, frame_pitch, width, height, stride=None, first_frame=0, stream=None):
+        stride = 3 * width if stride is None else stride
+        self._check(self._lib.nv12eq_synth_bgr_device(self._h, _ptr(d_out), n_frames, frame_pitch, width, height, stride,
+                                                      first_frame, _stream_ptr(stream)))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Reference-shaped operator interface (names and argument meaning of the OpenCV calls the reference makes)
+# ------------------------------------------------------------------------------------------------------------
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+def equalizeHist(nv12: np.ndarray, width: int, height: int, dst: Optional[np.ndarray] = None, uv_mode: int = UV_COPY,
+                 ctx: Optional[Context] = None) -> np.ndarray:
+    """``cv::equalizeHist(y_plane_in, y_plane_out)`` on the Y view of an NV12 buffer + chroma passthrough
+    (nextimprovement.cpp:159-168)."""
+    return (ctx or default_context()).equalize_hist(nv12, width, height, uv_mode=uv_mode, out=dst)
+
+
+class CLAHE:
+    """``cv::Ptr<cv::CLAHE>`` as the reference uses it (clahevideo.cpp:184-195): created once, ``apply`` per frame."""
+
+    def __init__(self, clipLimit: float = 40.0, tileGridSize: Sequence[int] = (8, 8), ctx: Optional[Context] = None):
+        self._clip = float(clipLimit)
+        self._tiles = (int(tileGridSize[0]), int(tileGridSize[1]))
+        self._ctx = ctx
+
+    def setClipLimit(self, clipLimit: float):
+        self._clip = float(clipLimit)
+
+    def getClipLimit(self) -> float:
+        return self._clip
+
+    def setTilesGridSize(self, tileGridSize: Sequence[int]):
+        self._tiles = (int(tileGridSize[0]), int(tileGridSize[1]))
+
+    def getTilesGridSize(self) -> Tuple[int, int]:
+        return self._tiles
+
+    def apply(self, nv12: np.ndarray, width: int, height: int, dst: Optional[np.ndarray] = None,
+              uv_mode: int = UV_COPY) -> np.ndarray:
+        return (self._ctx or default_context()).clahe(nv12, width, height, self._clip, self._tiles, uv_mode=uv_mode, out=dst)
+
+
+def createCLAHE(clipLimit: float = 40.0, tileGridSize: Sequence[int] = (8, 8), ctx: Optional[Context] = None) -> CLAHE:
+    """Same defaults as ``cv::createCLAHE`` (40.0, 8x8); the reference passes 2.0 / 8 (clahevideo.cpp:384-385)."""
+    return CLAHE(clipLimit, tileGridSize, ctx)

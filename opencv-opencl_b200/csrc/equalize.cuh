@@ -1,0 +1,284 @@
+// equalize.cuh -- global histogram equalization of the Y plane of a batch of NV12 frames, one launch per batch.
+//
+// Replaces cv::equalizeHist as called at nextimprovement.cpp:168 (hist -> LUT -> apply) together
+// with the NV12 rebuild around it (UV memcpy nextimprovement.cpp:160 / memset 128 OpenCVequalHist.cpp:162).
+//
+// Schedule ("ticket-lag"): work is cut into items drawn by CTAs from a global ticket counter, so items START
+// strictly in ticket order.  Slot g of the ticket space holds 2C items:
+//     r <  C : histogram chunk r of frame g           (if g < n_frames) -> smem hist[256][32] -> global hist[g][256]
+//     r >= C : LUT + apply + UV of chunk r-C of frame g - lag (if >= 0);  waits until all C histogram chunks of
+//              that frame have been added (done[f] == C)
+// A waiting CTA can only wait on items with smaller tickets, which are resident or finished, so the wait always
+// ends (any lag >= 0, any grid size).  With lag >= 1 a frame's histogram is complete before its apply items are
+// drawn, the Y plane it just streamed through is still in the 126 MB L2 when it is read the second time, and
+// atomics-bound histogram work and HBM-bound apply/copy work overlap on every SM.  The same kernel runs the plain two-launch schedule
+// (phases = HIST, then phases = APPLY) and the stage-level forms of the spatially split mode.
+//
+// Roofline: HBM.  Algorithmic bytes per frame = 3*W*H (read NV12 once, write NV12 once; the second read of Y is
+// expected to hit L2).  The secondary limiter is the LSU: one shared atomic and one shared gather per pixel.
+#pragma once
+#include "common.cuh"
+
+namespace nv12eq {
+
+enum : int { PH_HIST = 1, PH_APPLY = 2, PH_EXTERNAL_HIST = 4 };
+
+struct EqParams {
+    const uint8_t* in;
+    uint8_t* out;
+    unsigned long long pitch;  // bytes between frames
+    int n_frames;
+    int w, h, stride;
+    int flat;     // stride == w: planes are contiguous byte spans
+    int uv_mode;  // UV_COPY / UV_GRAY128 / UV_SKIP
+    int chunks;   // C, chunks per frame
+    int lag;      // frames between a frame's histogram items and its apply items
+    int phases;   // PH_* mask
+    unsigned long long y_bytes, uv_bytes;      // flat: W*H and W*(H/2)
+    unsigned long long y_chunk, uv_chunk;      // flat: bytes per chunk (multiples of 4096)
+    int y_rows_chunk, uv_rows_chunk;           // strided: rows per chunk
+    long long total_px;                        // pixel count the histogram describes (W*H unless spatially split)
+    uint32_t* hist;     // [n_frames][256], zero on entry; self-cleaned unless PH_EXTERNAL_HIST
+    uint32_t* done;     // [n_frames] histogram chunks added; self-cleaned
+    uint32_t* applied;  // [n_frames] apply chunks finished; self-cleaned
+    uint32_t* ticket;   // [1] work counter; self-cleaned
+    uint32_t* status;   // [1] sticky error word (spin timeout)
+};
+
+// One warp: 256-bin histogram (global) -> equalization LUT (shared), SURVEY.md A.1 / oracle_equalize_lut.
+__device__ __forceinline__ void equalize_lut_warp(const uint32_t* __restrict__ ghist, long long total,
+                                                  uint8_t* __restrict__ slut, int lane) {
+    uint32_t h[8];
+    const uint4* g4 = reinterpret_cast<const uint4*>(ghist) + lane * 2;
+    uint4 a = __ldcg(g4), b = __ldcg(g4 + 1);
+    h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+    uint32_t lsum = 0;
+    int first = 8;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+        lsum += h[j];
+        if (h[j] != 0) first = j;
+    }
+    const uint32_t nz = __ballot_sync(0xffffffffu, first < 8);
+    uint32_t incl = warp_incl_scan(lsum, lane);
+    if (nz == 0) {  // empty plane: nothing will be read from the LUT
+#pragma unroll
+        for (int j = 0; j < 8; ++j) slut[lane * 8 + j] = 0;
+        return;
+    }
+    const int l0 = __ffs(nz) - 1;
+    const int j0 = __shfl_sync(0xffffffffu, first, l0);
+    const int i0 = l0 * 8 + j0;
+    // cumulative count up to and including bin i0, and hist[i0]
+    uint32_t run = incl - lsum;  // exclusive prefix of this lane
+    uint32_t cum_i0_local = 0, h_i0_local = 0;
+    {
+        uint32_t r = run;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            r += h[j];
+            if (j == j0) { cum_i0_local = r; h_i0_local = h[j]; }
+        }
+    }
+    const uint32_t cum_i0 = __shfl_sync(0xffffffffu, cum_i0_local, l0);
+    const uint32_t h_i0 = __shfl_sync(0xffffffffu, h_i0_local, l0);
+    if ((long long)h_i0 == total) {  // constant image: dst = i0 everywhere
+#pragma unroll
+        for (int j = 0; j < 8; ++j) slut[lane * 8 + j] = (uint8_t)i0;
+        return;
+    }
+    const float scale = __fdiv_rn(255.0f, (float)(total - (long long)h_i0));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        run += h[j];
+        const int i = lane * 8 + j;
+        uint32_t v = 0;
+        if (i > i0) v = round_sat_u8(__fmul_rn(__uint2float_rn(run - cum_i0), scale));
+        slut[i] = (uint8_t)v;
+    }
+}
+
+// Chunk c of a plane of `rows` rows.  Flat planes are cut by bytes, strided planes by rows.
+struct PlaneChunk {
+    unsigned long long b0, b1;  // flat: byte range
+    int r0, r1;                 // strided: row range
+};
+__device__ __forceinline__ PlaneChunk plane_chunk(int flat, int c, unsigned long long bytes, unsigned long long chunk,
+                                                  int rows, int rows_chunk) {
+    PlaneChunk pc;
+    if (flat) {
+        pc.b0 = min((unsigned long long)c * chunk, bytes);
+        pc.b1 = min(pc.b0 + chunk, bytes);
+        pc.r0 = pc.r1 = 0;
+    } else {
+        pc.b0 = pc.b1 = 0;
+        pc.r0 = min(c * rows_chunk, rows);
+        pc.r1 = min(pc.r0 + rows_chunk, rows);
+    }
+    return pc;
+}
+
+__global__ void __launch_bounds__(kThreads, 3) equalize_kernel(const EqParams p) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* s_hist = smem;                     // [256][32]
+    uint32_t* s_table = smem + kLaneTableWords;  // [256][32]
+    __shared__ __align__(16) uint8_t s_lut[256];
+    __shared__ uint32_t s_item;
+    __shared__ int s_flag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const LaneTable hist_lane{reinterpret_cast<char*>(s_hist), (uint32_t)lane * 4u};
+    const LaneTable table_lane{reinterpret_cast<char*>(s_table), (uint32_t)lane * 4u};
+    const int C = p.chunks;
+    const bool do_hist = (p.phases & PH_HIST) != 0, do_apply = (p.phases & PH_APPLY) != 0;
+    const bool external = (p.phases & PH_EXTERNAL_HIST) != 0;
+    const int lag = (do_hist && do_apply) ? p.lag : 0;
+    const uint32_t total_items = (uint32_t)(p.n_frames + lag) * (uint32_t)(2 * C);
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        __syncthreads();
+        if (item >= total_items) {
+            // every CTA fails exactly once; the last failure resets the counter for the next launch
+            if (tid == 0 && item == total_items + gridDim.x - 1) atomicExch(p.ticket, 0u);
+            break;
+        }
+        const int g = (int)(item / (uint32_t)(2 * C));
+        const int r2 = (int)(item % (uint32_t)(2 * C));
+        const bool hist_item = r2 < C;
+        const int c = hist_item ? r2 : r2 - C;
+
+        // ---------------- histogram of chunk c of frame g ----------------
+        if (hist_item && do_hist && g < p.n_frames) {
+            const uint8_t* y = p.in + (unsigned long long)g * p.pitch;
+            lane_table_zero(s_hist);
+            __syncthreads();
+            const PlaneChunk pc = plane_chunk(p.flat, c, p.y_bytes, p.y_chunk, p.h, p.y_rows_chunk);
+            if (p.flat) {
+                hist_span<4>(y + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, hist_lane);
+            } else {
+                for (int r = pc.r0 + warp; r < pc.r1; r += kWarps)
+                    hist_span<2>(y + (size_t)r * p.stride, (size_t)p.w, lane, 32, hist_lane);
+            }
+            __syncthreads();
+            const uint32_t cnt = lane_table_row_sum(s_hist, tid);
+            if (cnt) atomicAdd(p.hist + (size_t)g * 256 + tid, cnt);
+            if (!external) {
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) atomicAdd(p.done + g, 1u);
+            } else {
+                __syncthreads();
+            }
+        }
+
+        // ---------------- LUT + apply + UV for chunk c of frame f ----------------
+        const int f = g - lag;
+        if (!hist_item && do_apply && f >= 0) {
+            if (!external) {
+                if (tid == 0) {
+                    bool ok = spin_until_ge(p.done + f, (uint32_t)C);
+                    if (!ok) atomicExch(p.status, 1u);
+                    s_flag = ok;
+                }
+                __syncthreads();
+                if (!s_flag) break;
+            }
+            if (warp == 0) equalize_lut_warp(p.hist + (size_t)f * 256, p.total_px, s_lut, lane);
+            __syncthreads();
+            lane_table_fill_from_lut(s_table, s_lut);
+            __syncthreads();
+
+            const uint8_t* src = p.in + (unsigned long long)f * p.pitch;
+            uint8_t* dst = p.out + (unsigned long long)f * p.pitch;
+            const PlaneChunk pc = plane_chunk(p.flat, c, p.y_bytes, p.y_chunk, p.h, p.y_rows_chunk);
+            if (p.flat) {
+                lut_span<4>(src + pc.b0, dst + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, table_lane);
+            } else {
+                for (int r = pc.r0 + warp; r < pc.r1; r += kWarps)
+                    lut_span<2>(src + (size_t)r * p.stride, dst + (size_t)r * p.stride, (size_t)p.w, lane, 32, table_lane);
+            }
+            // chroma rows
+            const bool copy_uv = p.uv_mode == UV_COPY && src != dst;
+            if (copy_uv || p.uv_mode == UV_GRAY128) {
+                const size_t uv_off = (size_t)p.stride * p.h;
+                const PlaneChunk uc = plane_chunk(p.flat, c, p.uv_bytes, p.uv_chunk, p.h / 2, p.uv_rows_chunk);
+                if (p.flat) {
+                    const size_t n = (size_t)(uc.b1 - uc.b0);
+                    if (copy_uv) copy_span<4>(src + uv_off + uc.b0, dst + uv_off + uc.b0, n, tid, kThreads);
+                    else fill_span(dst + uv_off + uc.b0, n, tid, kThreads, 128);
+                } else {
+                    for (int r = uc.r0 + warp; r < uc.r1; r += kWarps) {
+                        const size_t off = uv_off + (size_t)r * p.stride;
+                        if (copy_uv) copy_span<2>(src + off, dst + off, (size_t)p.w, lane, 32);
+                        else fill_span(dst + off, (size_t)p.w, lane, 32, 128);
+                    }
+                }
+            }
+            if (!external) {
+                // last apply chunk of the frame returns the workspace to its zero state
+                __syncthreads();
+                if (tid == 0) s_flag = (atomicAdd(p.applied + f, 1u) == (uint32_t)(C - 1));
+                __syncthreads();
+                if (s_flag) {
+                    p.hist[(size_t)f * 256 + tid] = 0;
+                    if (tid == 0) { p.done[f] = 0; p.applied[f] = 0; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- Appendix B synthetic frames, generated on the device (bench / test utility) -------------------------
+__global__ void __launch_bounds__(kThreads) synth_nv12_kernel(uint8_t* out, unsigned long long pitch, int w, int h,
+                                                              int stride, uint32_t seed, uint32_t first_frame) {
+    const int f = blockIdx.y;
+    uint8_t* base = out + (unsigned long long)f * pitch;
+    const uint32_t frame = first_frame + (uint32_t)f;
+    const int rows = h + h / 2;
+    const int bw = max(w / 16, 1), bh = max(h / 9, 1);
+    const long long total = (long long)rows * w;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const int r = (int)(i / w), c = (int)(i - (long long)r * w);
+        uint8_t v;
+        if (r < h) {
+            const uint32_t idx = (uint32_t)r * (uint32_t)w + (uint32_t)c;
+            const uint32_t k = fmix32(idx * 0x9E3779B1u + seed * 0x85EBCA77u + frame * 0xC2B2AE3Du);
+            int base_v = 48 + (c * 128) / w + (r * 48) / h;
+            int noise = (int)(k & 63u) - 32;
+            if (((c / bw) + (r / bh)) % 5 == 0) { base_v = 200; noise = (int)(k & 3u); }
+            v = (uint8_t)min(max(base_v + noise, 0), 255);
+        } else {
+            const uint32_t j = (uint32_t)(r - h) * (uint32_t)w + (uint32_t)c;
+            const uint32_t k = fmix32(j * 0x9E3779B1u + seed + 0x01234567u + frame * 0xC2B2AE3Du);
+            v = (uint8_t)(128 + (int)(k & 31u) - 16);
+        }
+        base[(size_t)r * stride + c] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) synth_bgr_kernel(uint8_t* out, unsigned long long pitch, int w, int h,
+                                                             int stride, uint32_t first_frame) {
+    const int f = blockIdx.y;
+    uint8_t* base = out + (unsigned long long)f * pitch;
+    const uint32_t frame = first_frame + (uint32_t)f;
+    const int bw = max(w / 16, 1), bh = max(h / 9, 1);
+    const long long total = (long long)h * w * 3;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        const long long px = i / 3;
+        const int ch = (int)(i - px * 3);
+        const int r = (int)(px / w), c = (int)(px - (long long)r * w);
+        const uint32_t seed = 3026u + 1000u * (uint32_t)ch;
+        const uint32_t idx = (uint32_t)r * (uint32_t)w + (uint32_t)c;
+        const uint32_t k = fmix32(idx * 0x9E3779B1u + seed * 0x85EBCA77u + frame * 0xC2B2AE3Du);
+        int base_v = 48 + (c * 128) / w + (r * 48) / h;
+        int noise = (int)(k & 63u) - 32;
+        if (((c / bw) + (r / bh)) % 5 == 0) { base_v = 200; noise = (int)(k & 3u); }
+        base[(size_t)r * stride + (size_t)c * 3 + ch] = (uint8_t)min(max(base_v + noise, 0), 255);
+    }
+}
+
+}  // namespace nv12eq

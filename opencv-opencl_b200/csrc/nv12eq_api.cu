@@ -1,0 +1,890 @@
+// nv12eq_api.cu -- context, launch planning and the C-ABI of libnv12eq.so (see include/nv12eq.h).
+//
+// Host-side structure (replaces the reference's per-worker device context + blocking transfer protocol,
+// OpenCLequalHist.cpp:63-81,106-192,349-365):
+//   * one nv12eq_ctx per calling thread; it owns a "lane" per slot: a CUDA stream, device in/out buffers, pinned
+//     staging buffers (only used when the caller's memory is pageable) and a private kernel workspace, all cached
+//     by size.  H2D -> kernel -> D2H of one lane are stream-ordered; different lanes overlap, which gives the
+//     double-buffered upload / compute / download pipeline the MPSoC zero-copy path is replaced with.
+//   * device-resident entry points use a separate workspace and the caller's stream.
+// There is no CPU implementation anywhere in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/nv12eq.h"
+#include "clahe.cuh"
+#include "color.cuh"
+#include "equalize.cuh"
+
+using namespace nv12eq;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// Kernel workspace: counters that the kernels return to zero themselves (see equalize.cuh / clahe.cuh).
+struct Workspace {
+    DevBuf hist;      // [frames][256] u32
+    DevBuf counters;  // [3][frames] u32: done/tiles_done, applied, (spare)
+    DevBuf misc;      // ticket (u32 @0), status (u32 @4)
+    DevBuf luts;      // clahe: [frames][tiles][256] u8
+    DevBuf cells;     // clahe: int4 xcells[], ycells[]
+    DevBuf luma;      // colour: [2][frames][h][w]
+    int frames_cap = 0;
+    // cached CLAHE geometry
+    int gw = 0, gh = 0, gtx = 0, gty = 0, nxc = 0, nyc = 0;
+};
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf d_in, d_out;
+    HostBuf h_in, h_out;
+    Workspace ws;
+    // pending job
+    bool busy = false;
+    uint8_t* user_out = nullptr;     // when non-null, wait() copies h_out -> user_out (pageable output)
+    size_t out_bytes = 0;
+    int frames = 0;
+    uint32_t* h_status = nullptr;    // pinned 4 bytes
+};
+
+struct Plan {
+    int w, h, stride, n;
+    size_t pitch;
+    bool flat;
+};
+
+}  // namespace
+
+struct nv12eq_ctx {
+    int device = 0;
+    int max_w = 0, max_h = 0;
+    int sm_count = 0;
+    int tune_chunks = 0, tune_lag = 0, tune_ctas = 0, tune_schedule = 0;
+    std::vector<Lane> lanes;
+    cudaStream_t own_stream = nullptr;
+    Workspace dev_ws;  // for *_device entry points
+    std::string last_error;
+    nv12eq_counters ctr{};
+    bool attrs_set = false;
+};
+
+namespace {
+
+int fail(nv12eq_ctx* ctx, int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        ctx->last_error = buf;
+        ctx->ctr.errors++;
+    } else {
+        g_create_error = buf;
+    }
+    return status;
+}
+
+#define CK(ctx, call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess) {                                                                           \
+            int st__ = (e__ == cudaErrorMemoryAllocation) ? NV12EQ_ERR_OUT_OF_MEMORY : NV12EQ_ERR_CUDA;     \
+            return fail(ctx, st__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                   \
+    } while (0)
+
+int dev_reserve(nv12eq_ctx* ctx, DevBuf& b, size_t bytes, bool zero) {
+    if (b.cap >= bytes && b.p) return NV12EQ_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t cap = std::max<size_t>(bytes, 256);
+    CK(ctx, cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    if (zero) {
+        // cudaMemset runs on the legacy default stream, which non-blocking streams do not wait for
+        CK(ctx, cudaMemset(b.p, 0, cap));
+        CK(ctx, cudaStreamSynchronize(0));
+    }
+    return NV12EQ_OK;
+}
+int host_reserve(nv12eq_ctx* ctx, HostBuf& b, size_t bytes) {
+    if (b.cap >= bytes && b.p) return NV12EQ_OK;
+    if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+    CK(ctx, cudaHostAlloc(&b.p, bytes, cudaHostAllocDefault));
+    b.cap = bytes;
+    return NV12EQ_OK;
+}
+void dev_release(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+void host_release(HostBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+
+void ws_release(Workspace& w) {
+    dev_release(w.hist); dev_release(w.counters); dev_release(w.misc); dev_release(w.luts); dev_release(w.cells);
+    dev_release(w.luma);
+    w.frames_cap = 0; w.gw = w.gh = w.gtx = w.gty = 0;
+}
+
+// Counters are (re)allocated zeroed; the kernels keep them zero between launches.
+int ws_reserve_frames(nv12eq_ctx* ctx, Workspace& w, int frames) {
+    if (!w.misc.p) {
+        int rc = dev_reserve(ctx, w.misc, 256, true);
+        if (rc) return rc;
+    }
+    if (frames <= w.frames_cap) return NV12EQ_OK;
+    int cap = std::max(frames, 16);
+    dev_release(w.hist); dev_release(w.counters);
+    int rc = dev_reserve(ctx, w.hist, (size_t)cap * 256 * sizeof(uint32_t), true);
+    if (rc) return rc;
+    rc = dev_reserve(ctx, w.counters, (size_t)cap * 3 * sizeof(uint32_t), true);
+    if (rc) return rc;
+    w.frames_cap = cap;
+    return NV12EQ_OK;
+}
+uint32_t* ws_counter(Workspace& w, int which) { return reinterpret_cast<uint32_t*>(w.counters.p) + (size_t)which * w.frames_cap; }
+uint32_t* ws_ticket(Workspace& w) { return reinterpret_cast<uint32_t*>(w.misc.p); }
+uint32_t* ws_status(Workspace& w) { return reinterpret_cast<uint32_t*>(w.misc.p) + 1; }
+
+int ensure_attrs(nv12eq_ctx* ctx) {
+    if (ctx->attrs_set) return NV12EQ_OK;
+    CK(ctx, cudaFuncSetAttribute(equalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(clahe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    ctx->attrs_set = true;
+    return NV12EQ_OK;
+}
+
+int check_geometry(nv12eq_ctx* ctx, int w, int h, int stride, int n, size_t pitch, int uv_mode) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (w <= 0 || h <= 0 || stride < w || n < 0) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad geometry w=%d h=%d stride=%d n=%d", w, h, stride, n);
+    if (uv_mode < 0 || uv_mode > 2) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad uv_mode %d", uv_mode);
+    if ((long long)w * h >= (1ll << 31)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "frame has 2^31 pixels or more");
+    if (w > ctx->max_w || h > ctx->max_h) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "frame %dx%d exceeds context maximum %dx%d", w, h, ctx->max_w, ctx->max_h);
+    size_t need = (size_t)stride * (size_t)(h + h / 2);
+    if (n > 1 && pitch < need) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "frame_pitch %zu < frame size %zu", pitch, need);
+    return NV12EQ_OK;
+}
+
+int grid_for(nv12eq_ctx* ctx, long long items, int default_ctas) {
+    int per_sm = ctx->tune_ctas > 0 ? ctx->tune_ctas : default_ctas;
+    long long g = (long long)ctx->sm_count * per_sm;
+    return (int)std::max<long long>(1, std::min<long long>(g, items));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// equalizeHist launch planning
+// ---------------------------------------------------------------------------------------------------------
+int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d_out, int n, size_t pitch, int w,
+                    int h, int stride, int uv_mode, cudaStream_t st, int phases_override = 0, uint32_t* ext_hist = nullptr,
+                    long long total_px = 0) {
+    if (n == 0) return NV12EQ_OK;
+    int rc = ensure_attrs(ctx);
+    if (rc) return rc;
+    rc = ws_reserve_frames(ctx, ws, n);
+    if (rc) return rc;
+
+    EqParams p{};
+    p.in = d_in; p.out = d_out; p.pitch = pitch; p.n_frames = n;
+    p.w = w; p.h = h; p.stride = stride; p.flat = (stride == w);
+    p.uv_mode = uv_mode;
+    p.y_bytes = (unsigned long long)w * h;
+    p.uv_bytes = (unsigned long long)w * (h / 2);
+    p.total_px = total_px ? total_px : (long long)w * h;
+
+    // chunks per frame: ~128 KB of luma per item, but never fewer items than ~2 waves of CTAs
+    const int ctas = ctx->sm_count * (ctx->tune_ctas > 0 ? ctx->tune_ctas : 3);
+    long long C = (long long)((p.y_bytes + 131071) / 131072);
+    if (ctx->tune_chunks > 0) C = ctx->tune_chunks;
+    else if ((long long)n * C < 2ll * ctas) C = std::min<long long>((2ll * ctas + n - 1) / n, (long long)((p.y_bytes + 16383) / 16384));
+    C = std::max<long long>(1, std::min<long long>(C, 1 << 16));
+    if (!p.flat) C = std::min<long long>(C, h);
+    p.chunks = (int)C;
+    auto round4k = [](unsigned long long v) { return (v + 4095ull) & ~4095ull; };
+    p.y_chunk = std::max<unsigned long long>(4096, round4k((p.y_bytes + C - 1) / C));
+    p.uv_chunk = std::max<unsigned long long>(4096, round4k((p.uv_bytes + C - 1) / C));
+    p.y_rows_chunk = (int)((h + C - 1) / C);
+    p.uv_rows_chunk = (int)((h / 2 + C - 1) / C);
+    p.lag = ctx->tune_lag > 0 ? ctx->tune_lag : 2;
+    if (ctx->tune_lag < 0) p.lag = 0;
+    p.lag = std::min(p.lag, std::max(n - 1, 0));
+    p.hist = ext_hist ? ext_hist : reinterpret_cast<uint32_t*>(ws.hist.p);
+    p.done = ws_counter(ws, 0);
+    p.applied = ws_counter(ws, 1);
+    p.ticket = ws_ticket(ws);
+    p.status = ws_status(ws);
+
+    const size_t smem = 2 * kLaneTableBytes;
+    auto go = [&](int phases) -> int {
+        p.phases = phases;
+        const bool both = (phases & PH_HIST) && (phases & PH_APPLY);
+        long long items = (long long)(n + (both ? p.lag : 0)) * 2 * C;
+        int grid = grid_for(ctx, items, 3);
+        equalize_kernel<<<grid, kThreads, smem, st>>>(p);
+        ctx->ctr.kernel_launches++;
+        CK(ctx, cudaGetLastError());
+        return NV12EQ_OK;
+    };
+    if (phases_override) return go(phases_override);
+    if (ctx->tune_schedule == 2) {
+        rc = go(PH_HIST);
+        if (rc) return rc;
+        return go(PH_APPLY);
+    }
+    return go(PH_HIST | PH_APPLY);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CLAHE launch planning
+// ---------------------------------------------------------------------------------------------------------
+struct ClaheGeom {
+    int extW, extH, tw, th, clip_limit;
+    float lut_scale, inv_tw, inv_th;
+};
+
+ClaheGeom clahe_geometry(int w, int h, double clip, int tx, int ty) {
+    ClaheGeom g{};
+    g.extW = w; g.extH = h;
+    if (w % tx != 0 || h % ty != 0) {  // OpenCV pads BOTH dimensions, even the one that divides
+        g.extW = w + (tx - (w % tx));
+        g.extH = h + (ty - (h % ty));
+    }
+    g.tw = g.extW / tx; g.th = g.extH / ty;
+    const int area = g.tw * g.th;
+    g.clip_limit = 0;
+    if (clip > 0.0) g.clip_limit = std::max(1, (int)(clip * area / 256.0));
+    g.lut_scale = 255.0f / (float)area;
+    g.inv_tw = 1.0f / (float)g.tw;
+    g.inv_th = 1.0f / (float)g.th;
+    return g;
+}
+
+// Interpolation cells along one axis: maximal runs of positions with the same floor(pos*inv - 0.5), cut into pieces
+// of at most max_len so that one cell is one CTA-sized item.
+void axis_cells(int n, float inv, int ntiles, int max_len, int align, std::vector<int4>& out) {
+    out.clear();
+    int start = 0;
+    auto t1_of = [&](int pos) {
+        volatile float f = (float)pos * inv;  // separately rounded multiply and subtract, as on the device
+        volatile float g = f - 0.5f;
+        return (int)floorf(g);
+    };
+    int cur = t1_of(0);
+    auto flush = [&](int s, int e, int t1) {
+        const int a = std::max(t1, 0), b = std::min(t1 + 1, ntiles - 1);
+        int pos = s;
+        while (pos < e) {
+            int len = std::min(max_len, e - pos);
+            if (pos + len < e && align > 1) {  // keep interior cuts aligned
+                int cut = ((pos + len) / align) * align;
+                if (cut > pos) len = cut - pos;
+            }
+            out.push_back(make_int4(pos, pos + len, a, b));
+            pos += len;
+        }
+    };
+    for (int pos = 1; pos < n; ++pos) {
+        const int t = t1_of(pos);
+        if (t != cur) { flush(start, pos, cur); start = pos; cur = t; }
+    }
+    flush(start, n, cur);
+}
+
+int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d_out, int n, size_t pitch, int w, int h,
+                 int stride, double clip, int tx, int ty, int uv_mode, cudaStream_t st) {
+    if (n == 0) return NV12EQ_OK;
+    if (tx < 1 || ty < 1 || (long long)tx * ty > (1 << 20)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", tx, ty);
+    int rc = ensure_attrs(ctx);
+    if (rc) return rc;
+    rc = ws_reserve_frames(ctx, ws, n);
+    if (rc) return rc;
+    const ClaheGeom g = clahe_geometry(w, h, clip, tx, ty);
+    const int T = tx * ty;
+    rc = dev_reserve(ctx, ws.luts, (size_t)n * T * 256, false);
+    if (rc) return rc;
+    if (ws.gw != w || ws.gh != h || ws.gtx != tx || ws.gty != ty || !ws.cells.p) {
+        std::vector<int4> xc, yc;
+        axis_cells(w, g.inv_tw, tx, 1024, 8, xc);
+        axis_cells(h, g.inv_th, ty, 512, 1, yc);
+        rc = dev_reserve(ctx, ws.cells, (xc.size() + yc.size()) * sizeof(int4), false);
+        if (rc) return rc;
+        // stream-ordered after any kernel still reading the previous tables; the pageable source makes the call
+        // return only after the bytes have been staged
+        CK(ctx, cudaMemcpyAsync(ws.cells.p, xc.data(), xc.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        CK(ctx, cudaMemcpyAsync(reinterpret_cast<int4*>(ws.cells.p) + xc.size(), yc.data(), yc.size() * sizeof(int4),
+                                cudaMemcpyHostToDevice, st));
+        ws.gw = w; ws.gh = h; ws.gtx = tx; ws.gty = ty;
+        ws.nxc = (int)xc.size(); ws.nyc = (int)yc.size();
+    }
+
+    ClaheParams p{};
+    p.in = d_in; p.out = d_out; p.pitch = pitch; p.n_frames = n;
+    p.w = w; p.h = h; p.stride = stride; p.flat = (stride == w); p.uv_mode = uv_mode;
+    p.tx = tx; p.ty = ty; p.tw = g.tw; p.th = g.th;
+    p.padded = (g.extW != w || g.extH != h);
+    p.clip_limit = g.clip_limit; p.lut_scale = g.lut_scale; p.inv_tw = g.inv_tw; p.inv_th = g.inv_th;
+    p.nxc = ws.nxc; p.nyc = ws.nyc;
+    p.xcells = reinterpret_cast<const int4*>(ws.cells.p);
+    p.ycells = p.xcells + ws.nxc;
+    const bool uv_work = (uv_mode == UV_GRAY128) || (uv_mode == UV_COPY && d_in != d_out);
+    p.uv_bytes = (unsigned long long)w * (h / 2);
+    int U = 0;
+    if (uv_work && h / 2 > 0) {
+        U = (int)std::max<unsigned long long>(1, (p.uv_bytes + 131071) / 131072);
+        if (!p.flat) U = std::min(U, h / 2);
+        p.uv_chunk = std::max<unsigned long long>(4096, (((p.uv_bytes + U - 1) / U) + 4095ull) & ~4095ull);
+        p.uv_rows_chunk = (h / 2 + U - 1) / U;
+    }
+    p.uv_chunks = U;
+    p.lag = ctx->tune_lag > 0 ? ctx->tune_lag : 1;
+    if (ctx->tune_lag < 0) p.lag = 0;
+    p.lag = std::min(p.lag, std::max(n - 1, 0));
+    p.luts = reinterpret_cast<uint8_t*>(ws.luts.p);
+    p.tiles_done = ws_counter(ws, 0);
+    p.applied = ws_counter(ws, 1);
+    p.ticket = ws_ticket(ws);
+    p.status = ws_status(ws);
+
+    const long long per_slot = (long long)T + (long long)p.nxc * p.nyc + U;
+    const long long items = (long long)(n + p.lag) * per_slot;
+    if (items >= (1ll << 32)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "too many work items");
+    const int grid = grid_for(ctx, items, 3);
+    clahe_kernel<<<grid, kThreads, kLaneTableBytes, st>>>(p);
+    ctx->ctr.kernel_launches++;
+    CK(ctx, cudaGetLastError());
+    return NV12EQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// colour path
+// ---------------------------------------------------------------------------------------------------------
+int launch_color(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d_out, int n, size_t pitch, int w, int h,
+                 int stride, int mode, bool use_clahe, double clip, int tx, int ty, cudaStream_t st) {
+    if (n == 0) return NV12EQ_OK;
+    const size_t plane = (size_t)w * h;
+    int rc = dev_reserve(ctx, ws.luma, 2 * plane * n + 64, false);
+    if (rc) return rc;
+    uint8_t* y1 = reinterpret_cast<uint8_t*>(ws.luma.p);
+    uint8_t* y2 = y1 + ((plane * n + 15) & ~(size_t)15);
+    ColorParams cp{};
+    cp.bgr_in = d_in; cp.bgr_out = d_out; cp.bgr_pitch = pitch; cp.n_frames = n;
+    cp.w = w; cp.h = h; cp.stride = stride; cp.y_plane = y1; cp.y2_plane = y2; cp.mode = mode;
+    const long long quads = ((long long)plane + 3) / 4;
+    const int gx = (int)std::max<long long>(1, std::min<long long>((quads + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8));
+    dim3 grid(gx, n);
+    bgr_to_luma_kernel<<<grid, kThreads, 0, st>>>(cp);
+    ctx->ctr.kernel_launches++;
+    CK(ctx, cudaGetLastError());
+    // the luma planes are Y-only "frames" of pitch w*h: stride == w, chroma skipped
+    if (use_clahe) rc = launch_clahe(ctx, ws, y1, y2, n, plane, w, h, w, clip, tx, ty, UV_SKIP, st);
+    else rc = launch_equalize(ctx, ws, y1, y2, n, plane, w, h, w, UV_SKIP, st);
+    if (rc) return rc;
+    bgr_recombine_kernel<<<grid, kThreads, 0, st>>>(cp);
+    ctx->ctr.kernel_launches++;
+    CK(ctx, cudaGetLastError());
+    return NV12EQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host lanes
+// ---------------------------------------------------------------------------------------------------------
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+enum class Op { Equalize, Clahe, ColorEq, ColorClahe };
+struct Job {
+    Op op;
+    const uint8_t* in; uint8_t* out;
+    int n; size_t pitch; size_t frame_bytes;
+    int w, h, stride, uv_mode;
+    double clip; int tx, ty; int color_mode;
+};
+
+int lane_submit(nv12eq_ctx* ctx, Lane& L, const Job& j) {
+    if (L.busy) return fail(ctx, NV12EQ_ERR_BAD_SLOT, "slot is busy; call nv12eq_wait first");
+    if (j.n == 0) return NV12EQ_OK;
+    const size_t span = (size_t)(j.n - 1) * j.pitch + j.frame_bytes;  // bytes covered in the caller's buffers
+    int rc;
+    if ((rc = dev_reserve(ctx, L.d_in, span, false))) return rc;
+    const bool in_place = (j.in == j.out);
+    if (!in_place && (rc = dev_reserve(ctx, L.d_out, span, false))) return rc;
+    uint8_t* d_in = reinterpret_cast<uint8_t*>(L.d_in.p);
+    uint8_t* d_out = in_place ? d_in : reinterpret_cast<uint8_t*>(L.d_out.p);
+
+    const uint8_t* src = j.in;
+    if (!is_pinned(j.in)) {  // pageable caller memory: stage through pinned memory so the DMA is asynchronous
+        if ((rc = host_reserve(ctx, L.h_in, span))) return rc;
+        memcpy(L.h_in.p, j.in, span);
+        src = reinterpret_cast<const uint8_t*>(L.h_in.p);
+    }
+    CK(ctx, cudaMemcpyAsync(d_in, src, span, cudaMemcpyHostToDevice, L.stream));
+    ctx->ctr.bytes_in += span;
+    // With UV_SKIP the caller's existing output chroma must survive; with strided frames the padding bytes must
+    // survive too.  In both cases the device output image has to start from the caller's output bytes.
+    const bool preserve_out = !in_place && (j.uv_mode == UV_SKIP || j.stride != j.w || j.pitch != j.frame_bytes) &&
+                              (j.op == Op::Equalize || j.op == Op::Clahe);
+    const bool preserve_bgr = !in_place && (j.op == Op::ColorEq || j.op == Op::ColorClahe) && (j.stride != 3 * j.w);
+    if (preserve_out || preserve_bgr) {
+        const uint8_t* osrc = j.out;
+        if (!is_pinned(j.out)) {
+            if ((rc = host_reserve(ctx, L.h_out, span))) return rc;
+            memcpy(L.h_out.p, j.out, span);
+            osrc = reinterpret_cast<const uint8_t*>(L.h_out.p);
+        }
+        CK(ctx, cudaMemcpyAsync(d_out, osrc, span, cudaMemcpyHostToDevice, L.stream));
+        ctx->ctr.bytes_in += span;
+    }
+    switch (j.op) {
+        case Op::Equalize:
+            rc = launch_equalize(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.uv_mode, L.stream);
+            break;
+        case Op::Clahe:
+            rc = launch_clahe(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.clip, j.tx, j.ty, j.uv_mode, L.stream);
+            break;
+        case Op::ColorEq:
+        case Op::ColorClahe:
+            rc = launch_color(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.color_mode, j.op == Op::ColorClahe,
+                              j.clip, j.tx, j.ty, L.stream);
+            break;
+    }
+    if (rc) return rc;
+    uint8_t* dst = j.out;
+    L.user_out = nullptr;
+    if (!is_pinned(j.out)) {
+        if ((rc = host_reserve(ctx, L.h_out, span))) return rc;
+        dst = reinterpret_cast<uint8_t*>(L.h_out.p);
+        L.user_out = j.out;
+    }
+    CK(ctx, cudaMemcpyAsync(dst, d_out, span, cudaMemcpyDeviceToHost, L.stream));
+    CK(ctx, cudaMemcpyAsync(L.h_status, ws_status(L.ws), sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream));
+    CK(ctx, cudaEventRecord(L.done, L.stream));
+    ctx->ctr.bytes_out += span;
+    L.out_bytes = span;
+    L.frames = j.n;
+    L.busy = true;
+    return NV12EQ_OK;
+}
+
+int lane_wait(nv12eq_ctx* ctx, Lane& L) {
+    if (!L.busy) return NV12EQ_OK;
+    L.busy = false;
+    CK(ctx, cudaEventSynchronize(L.done));
+    if (*L.h_status != 0) {
+        // a kernel gave up waiting (should be impossible); put the workspace back to a known state
+        cudaMemsetAsync(L.ws.misc.p, 0, L.ws.misc.cap, L.stream);
+        if (L.ws.hist.p) cudaMemsetAsync(L.ws.hist.p, 0, L.ws.hist.cap, L.stream);
+        if (L.ws.counters.p) cudaMemsetAsync(L.ws.counters.p, 0, L.ws.counters.cap, L.stream);
+        cudaStreamSynchronize(L.stream);
+        return fail(ctx, NV12EQ_ERR_CUDA, "kernel dependency wait timed out");
+    }
+    if (L.user_out) memcpy(L.user_out, L.h_out.p, L.out_bytes);
+    L.user_out = nullptr;
+    ctx->ctr.frames += (uint64_t)L.frames;
+    return NV12EQ_OK;
+}
+
+int check_host_job(nv12eq_ctx* ctx, const Job& j) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (!j.in || !j.out) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "null frame pointer");
+    if (j.in != j.out) {
+        const size_t span = j.n > 0 ? (size_t)(j.n - 1) * j.pitch + j.frame_bytes : 0;
+        const uint8_t* a = j.in; const uint8_t* b = j.out;
+        if ((a < b && a + span > b) || (b < a && b + span > a)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "input and output overlap partially");
+    }
+    return NV12EQ_OK;
+}
+
+// Synchronous batch through two (or more) lanes: group k uses lane k % L, so the upload of one group overlaps the
+// kernels and the download of the previous one.
+int run_batch(nv12eq_ctx* ctx, Job j) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = check_host_job(ctx, j);
+    if (rc) return rc;
+    DeviceGuard guard(ctx->device);
+    const int nl = (int)ctx->lanes.size();
+    const size_t target = 64ull << 20;
+    int group = (int)std::max<size_t>(1, std::min<size_t>(64, target / std::max<size_t>(1, j.pitch)));
+    if (j.n <= group) group = std::max(1, (j.n + std::min(nl, j.n) - 1) / std::max(1, std::min(nl, j.n)));
+    int k = 0, first_err = NV12EQ_OK;
+    for (int f0 = 0; f0 < j.n; f0 += group, ++k) {
+        Lane& L = ctx->lanes[k % nl];
+        rc = lane_wait(ctx, L);
+        if (rc && !first_err) first_err = rc;
+        Job sub = j;
+        sub.n = std::min(group, j.n - f0);
+        sub.in = j.in + (size_t)f0 * j.pitch;
+        sub.out = j.out + (size_t)f0 * j.pitch;
+        rc = lane_submit(ctx, L, sub);
+        if (rc) { first_err = first_err ? first_err : rc; break; }
+    }
+    for (auto& L : ctx->lanes) {
+        rc = lane_wait(ctx, L);
+        if (rc && !first_err) first_err = rc;
+    }
+    ctx->ctr.busy_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    return first_err;
+}
+
+Job make_nv12_job(Op op, const uint8_t* in, uint8_t* out, int n, size_t pitch, int w, int h, int stride, int uv_mode,
+                  double clip, int tx, int ty) {
+    Job j{};
+    j.op = op; j.in = in; j.out = out; j.n = n;
+    j.frame_bytes = (size_t)stride * (size_t)(h + h / 2);
+    j.pitch = (n > 1 || pitch) ? pitch : j.frame_bytes;
+    if (j.pitch == 0) j.pitch = j.frame_bytes;
+    j.w = w; j.h = h; j.stride = stride; j.uv_mode = uv_mode; j.clip = clip; j.tx = tx; j.ty = ty;
+    return j;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// C-ABI
+// =========================================================================================================
+extern "C" {
+
+int nv12eq_version(void) { return NV12EQ_VERSION_MAJOR * 100 + NV12EQ_VERSION_MINOR; }
+
+const char* nv12eq_status_string(int s) {
+    switch (s) {
+        case NV12EQ_OK: return "ok";
+        case NV12EQ_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case NV12EQ_ERR_SHORT_BUFFER: return "buffer too small for the frame";
+        case NV12EQ_ERR_CUDA: return "CUDA error";
+        case NV12EQ_ERR_NO_DEVICE: return "no usable CUDA device";
+        case NV12EQ_ERR_OUT_OF_MEMORY: return "out of memory";
+        case NV12EQ_ERR_BAD_SLOT: return "bad or busy slot";
+        case NV12EQ_ERR_TOO_LARGE: return "frame too large";
+        default: return "unknown status";
+    }
+}
+
+const char* nv12eq_last_error_string(const nv12eq_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+
+int nv12eq_create(int device, int max_width, int max_height, int slots, nv12eq_ctx** out_ctx) {
+    if (!out_ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    if (max_width <= 0 || max_height <= 0 || slots < 1 || slots > 64) return fail(nullptr, NV12EQ_ERR_INVALID_ARGUMENT, "bad create arguments");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, NV12EQ_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(nullptr, NV12EQ_ERR_NO_DEVICE, "device %d out of range (0..%d)", device, count - 1);
+    int major = 0, sms = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (major != 10) return fail(nullptr, NV12EQ_ERR_NO_DEVICE, "device %d is compute capability %d.x; libnv12eq is built for sm_100a only", device, major);
+    nv12eq_ctx* ctx = new (std::nothrow) nv12eq_ctx();
+    if (!ctx) return NV12EQ_ERR_OUT_OF_MEMORY;
+    ctx->device = device; ctx->max_w = max_width; ctx->max_h = max_height; ctx->sm_count = sms;
+    DeviceGuard guard(device);
+    ctx->lanes.resize(slots);
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& L : ctx->lanes) {
+        ok = ok && cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&L.h_status), sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
+        if (ok) *L.h_status = 0;
+    }
+    if (!ok) {
+        fail(nullptr, NV12EQ_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        nv12eq_destroy(ctx);
+        return NV12EQ_ERR_CUDA;
+    }
+    *out_ctx = ctx;
+    return NV12EQ_OK;
+}
+
+void nv12eq_destroy(nv12eq_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    for (auto& L : ctx->lanes) {
+        if (L.stream) cudaStreamSynchronize(L.stream);
+        dev_release(L.d_in); dev_release(L.d_out); host_release(L.h_in); host_release(L.h_out);
+        ws_release(L.ws);
+        if (L.h_status) cudaFreeHost(L.h_status);
+        if (L.done) cudaEventDestroy(L.done);
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
+    ws_release(ctx->dev_ws);
+    delete ctx;
+}
+
+int nv12eq_get_counters(const nv12eq_ctx* ctx, nv12eq_counters* out) {
+    if (!ctx || !out) return NV12EQ_ERR_INVALID_ARGUMENT;
+    *out = ctx->ctr;
+    return NV12EQ_OK;
+}
+
+int nv12eq_set_tuning(nv12eq_ctx* ctx, int chunks_per_frame, int lag_frames, int ctas_per_sm, int schedule) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (chunks_per_frame < 0 || ctas_per_sm < 0 || ctas_per_sm > 8 || schedule < 0 || schedule > 2)
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tuning values");
+    ctx->tune_chunks = chunks_per_frame; ctx->tune_lag = lag_frames; ctx->tune_ctas = ctas_per_sm; ctx->tune_schedule = schedule;
+    return NV12EQ_OK;
+}
+
+int nv12eq_host_alloc(size_t bytes, void** out_ptr) {
+    if (!out_ptr || bytes == 0) return NV12EQ_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostAlloc(out_ptr, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); *out_ptr = nullptr; return e == cudaErrorMemoryAllocation ? NV12EQ_ERR_OUT_OF_MEMORY : NV12EQ_ERR_CUDA; }
+    return NV12EQ_OK;
+}
+int nv12eq_host_free(void* ptr) {
+    if (!ptr) return NV12EQ_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? NV12EQ_OK : NV12EQ_ERR_CUDA;
+}
+
+// ---- host frame / batch forms ---------------------------------------------------------------------------
+int nv12eq_equalize_hist(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, uint8_t* out, size_t out_size, int width,
+                         int height, int stride, int uv_mode) {
+    int rc = check_geometry(ctx, width, height, stride, 1, 0, uv_mode);
+    if (rc) return rc;
+    const size_t need = (size_t)stride * (size_t)(height + height / 2);
+    if (in_size < need || out_size < need) return fail(ctx, NV12EQ_ERR_SHORT_BUFFER, "buffer %zu/%zu bytes < frame %zu bytes", in_size, out_size, need);
+    return run_batch(ctx, make_nv12_job(Op::Equalize, in, out, 1, need, width, height, stride, uv_mode, 0, 0, 0));
+}
+
+int nv12eq_clahe(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, uint8_t* out, size_t out_size, int width, int height,
+                 int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode) {
+    int rc = check_geometry(ctx, width, height, stride, 1, 0, uv_mode);
+    if (rc) return rc;
+    if (tiles_x < 1 || tiles_y < 1) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", tiles_x, tiles_y);
+    const size_t need = (size_t)stride * (size_t)(height + height / 2);
+    if (in_size < need || out_size < need) return fail(ctx, NV12EQ_ERR_SHORT_BUFFER, "buffer %zu/%zu bytes < frame %zu bytes", in_size, out_size, need);
+    return run_batch(ctx, make_nv12_job(Op::Clahe, in, out, 1, need, width, height, stride, uv_mode, clip_limit, tiles_x, tiles_y));
+}
+
+int nv12eq_equalize_hist_batch(nv12eq_ctx* ctx, const uint8_t* in, uint8_t* out, int n_frames, size_t frame_pitch, int width,
+                               int height, int stride, int uv_mode) {
+    int rc = check_geometry(ctx, width, height, stride, n_frames, frame_pitch, uv_mode);
+    if (rc) return rc;
+    return run_batch(ctx, make_nv12_job(Op::Equalize, in, out, n_frames, frame_pitch, width, height, stride, uv_mode, 0, 0, 0));
+}
+
+int nv12eq_clahe_batch(nv12eq_ctx* ctx, const uint8_t* in, uint8_t* out, int n_frames, size_t frame_pitch, int width,
+                       int height, int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode) {
+    int rc = check_geometry(ctx, width, height, stride, n_frames, frame_pitch, uv_mode);
+    if (rc) return rc;
+    if (tiles_x < 1 || tiles_y < 1) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", tiles_x, tiles_y);
+    return run_batch(ctx, make_nv12_job(Op::Clahe, in, out, n_frames, frame_pitch, width, height, stride, uv_mode, clip_limit, tiles_x, tiles_y));
+}
+
+static int submit_common(nv12eq_ctx* ctx, int slot, const Job& j) {
+    if (slot < 0 || slot >= (int)ctx->lanes.size()) return fail(ctx, NV12EQ_ERR_BAD_SLOT, "slot %d out of range", slot);
+    int rc = check_host_job(ctx, j);
+    if (rc) return rc;
+    DeviceGuard guard(ctx->device);
+    return lane_submit(ctx, ctx->lanes[slot], j);
+}
+
+int nv12eq_submit_equalize_hist(nv12eq_ctx* ctx, int slot, const uint8_t* in, uint8_t* out, int n_frames, size_t frame_pitch,
+                                int width, int height, int stride, int uv_mode) {
+    int rc = check_geometry(ctx, width, height, stride, n_frames, frame_pitch, uv_mode);
+    if (rc) return rc;
+    return submit_common(ctx, slot, make_nv12_job(Op::Equalize, in, out, n_frames, frame_pitch, width, height, stride, uv_mode, 0, 0, 0));
+}
+
+int nv12eq_submit_clahe(nv12eq_ctx* ctx, int slot, const uint8_t* in, uint8_t* out, int n_frames, size_t frame_pitch, int width,
+                        int height, int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode) {
+    int rc = check_geometry(ctx, width, height, stride, n_frames, frame_pitch, uv_mode);
+    if (rc) return rc;
+    if (tiles_x < 1 || tiles_y < 1) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", tiles_x, tiles_y);
+    return submit_common(ctx, slot, make_nv12_job(Op::Clahe, in, out, n_frames, frame_pitch, width, height, stride, uv_mode, clip_limit, tiles_x, tiles_y));
+}
+
+int nv12eq_wait(nv12eq_ctx* ctx, int slot) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (slot < 0 || slot >= (int)ctx->lanes.size()) return fail(ctx, NV12EQ_ERR_BAD_SLOT, "slot %d out of range", slot);
+    DeviceGuard guard(ctx->device);
+    return lane_wait(ctx, ctx->lanes[slot]);
+}
+
+int nv12eq_query(nv12eq_ctx* ctx, int slot) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (slot < 0 || slot >= (int)ctx->lanes.size()) return fail(ctx, NV12EQ_ERR_BAD_SLOT, "slot %d out of range", slot);
+    Lane& L = ctx->lanes[slot];
+    if (!L.busy) return NV12EQ_OK;
+    DeviceGuard guard(ctx->device);
+    cudaError_t e = cudaEventQuery(L.done);
+    if (e == cudaSuccess) return NV12EQ_OK;
+    if (e == cudaErrorNotReady) { cudaGetLastError(); return NV12EQ_ERR_BAD_SLOT; }
+    return fail(ctx, NV12EQ_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+}
+
+// ---- device forms ---------------------------------------------------------------------------------------
+static cudaStream_t pick_stream(nv12eq_ctx* ctx, void* s) { return s ? reinterpret_cast<cudaStream_t>(s) : ctx->own_stream; }
+
+int nv12eq_equalize_hist_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t frame_pitch, int width,
+                                int height, int stride, int uv_mode, void* cuda_stream) {
+    int rc = check_geometry(ctx, width, height, stride, n_frames, frame_pitch, uv_mode);
+    if (rc) return rc;
+    if (!d_in || !d_out) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "null device pointer");
+    DeviceGuard guard(ctx->device);
+    rc = launch_equalize(ctx, ctx->dev_ws, d_in, d_out, n_frames, frame_pitch, width, height, stride, uv_mode, pick_stream(ctx, cuda_stream));
+    if (!rc) ctx->ctr.frames += (uint64_t)n_frames;
+    return rc;
+}
+
+int nv12eq_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t frame_pitch, int width,
+                        int height, int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode, void* cuda_stream) {
+    int rc = check_geometry(ctx, width, height, stride, n_frames, frame_pitch, uv_mode);
+    if (rc) return rc;
+    if (!d_in || !d_out) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "null device pointer");
+    DeviceGuard guard(ctx->device);
+    rc = launch_clahe(ctx, ctx->dev_ws, d_in, d_out, n_frames, frame_pitch, width, height, stride, clip_limit, tiles_x, tiles_y, uv_mode,
+                      pick_stream(ctx, cuda_stream));
+    if (!rc) ctx->ctr.frames += (uint64_t)n_frames;
+    return rc;
+}
+
+int nv12eq_sync(nv12eq_ctx* ctx) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    CK(ctx, cudaStreamSynchronize(ctx->own_stream));
+    return NV12EQ_OK;
+}
+
+int nv12eq_hist_device(nv12eq_ctx* ctx, const uint8_t* d_y, int n_planes, size_t plane_pitch, int width, int height, int stride,
+                       uint32_t* d_hist, void* cuda_stream) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (!d_y || !d_hist || width <= 0 || height <= 0 || stride < width || n_planes < 0) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (n_planes > 1 && plane_pitch < (size_t)stride * height) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "plane_pitch too small");
+    DeviceGuard guard(ctx->device);
+    return launch_equalize(ctx, ctx->dev_ws, d_y, nullptr, n_planes, plane_pitch, width, height, stride, UV_SKIP, pick_stream(ctx, cuda_stream),
+                           PH_HIST | PH_EXTERNAL_HIST, d_hist);
+}
+
+int nv12eq_equalize_apply_device(nv12eq_ctx* ctx, const uint8_t* d_y_in, uint8_t* d_y_out, int n_planes, size_t plane_pitch, int width,
+                                 int height, int stride, const uint32_t* d_hist, int64_t total_pixels, void* cuda_stream) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (!d_y_in || !d_y_out || !d_hist || width <= 0 || height <= 0 || stride < width || n_planes < 0 || total_pixels <= 0)
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (n_planes > 1 && plane_pitch < (size_t)stride * height) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "plane_pitch too small");
+    DeviceGuard guard(ctx->device);
+    return launch_equalize(ctx, ctx->dev_ws, d_y_in, d_y_out, n_planes, plane_pitch, width, height, stride, UV_SKIP,
+                           pick_stream(ctx, cuda_stream), PH_APPLY | PH_EXTERNAL_HIST, const_cast<uint32_t*>(d_hist), (long long)total_pixels);
+}
+
+// ---- colour path ----------------------------------------------------------------------------------------
+static int check_color(nv12eq_ctx* ctx, int w, int h, int stride, int mode) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (w <= 0 || h <= 0 || stride < 3 * w) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad BGR geometry w=%d h=%d stride=%d", w, h, stride);
+    if (mode != NV12EQ_COLOR_YUV && mode != NV12EQ_COLOR_YCRCB) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad color_mode %d", mode);
+    if ((long long)w * h >= (1ll << 31)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "frame has 2^31 pixels or more");
+    if (w > ctx->max_w || h > ctx->max_h) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "frame %dx%d exceeds context maximum %dx%d", w, h, ctx->max_w, ctx->max_h);
+    return NV12EQ_OK;
+}
+
+static Job make_color_job(Op op, const uint8_t* in, uint8_t* out, int w, int h, int stride, int mode, double clip, int tx, int ty) {
+    Job j{};
+    j.op = op; j.in = in; j.out = out; j.n = 1;
+    // tight span: the caller's buffer may end right after the last pixel of the last row
+    j.frame_bytes = (size_t)stride * (h - 1) + 3 * (size_t)w; j.pitch = j.frame_bytes;
+    j.w = w; j.h = h; j.stride = stride; j.uv_mode = UV_SKIP; j.color_mode = mode; j.clip = clip; j.tx = tx; j.ty = ty;
+    return j;
+}
+
+int nv12eq_color_equalize(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_out, int width, int height, int stride, int color_mode) {
+    int rc = check_color(ctx, width, height, stride, color_mode);
+    if (rc) return rc;
+    return run_batch(ctx, make_color_job(Op::ColorEq, bgr_in, bgr_out, width, height, stride, color_mode, 0, 0, 0));
+}
+
+int nv12eq_color_clahe(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_out, int width, int height, int stride, int color_mode,
+                       double clip_limit, int tiles_x, int tiles_y) {
+    int rc = check_color(ctx, width, height, stride, color_mode);
+    if (rc) return rc;
+    if (tiles_x < 1 || tiles_y < 1) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", tiles_x, tiles_y);
+    return run_batch(ctx, make_color_job(Op::ColorClahe, bgr_in, bgr_out, width, height, stride, color_mode, clip_limit, tiles_x, tiles_y));
+}
+
+int nv12eq_color_equalize_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t frame_pitch, int width,
+                                 int height, int stride, int color_mode, void* cuda_stream) {
+    int rc = check_color(ctx, width, height, stride, color_mode);
+    if (rc) return rc;
+    if (!d_in || !d_out || n_frames < 0 || (n_frames > 1 && frame_pitch < (size_t)stride * height)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    DeviceGuard guard(ctx->device);
+    rc = launch_color(ctx, ctx->dev_ws, d_in, d_out, n_frames, frame_pitch, width, height, stride, color_mode, false, 0, 0, 0,
+                      pick_stream(ctx, cuda_stream));
+    if (!rc) ctx->ctr.frames += (uint64_t)n_frames;
+    return rc;
+}
+
+int nv12eq_color_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t frame_pitch, int width,
+                              int height, int stride, int color_mode, double clip_limit, int tiles_x, int tiles_y, void* cuda_stream) {
+    int rc = check_color(ctx, width, height, stride, color_mode);
+    if (rc) return rc;
+    if (!d_in || !d_out || n_frames < 0 || (n_frames > 1 && frame_pitch < (size_t)stride * height)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (tiles_x < 1 || tiles_y < 1) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", tiles_x, tiles_y);
+    DeviceGuard guard(ctx->device);
+    rc = launch_color(ctx, ctx->dev_ws, d_in, d_out, n_frames, frame_pitch, width, height, stride, color_mode, true, clip_limit, tiles_x,
+                      tiles_y, pick_stream(ctx, cuda_stream));
+    if (!rc) ctx->ctr.frames += (uint64_t)n_frames;
+    return rc;
+}
+
+// ---- synthetic inputs -----------------------------------------------------------------------------------
+int nv12eq_synth_nv12_device(nv12eq_ctx* ctx, uint8_t* d_out, int n_frames, size_t frame_pitch, int width, int height, int stride,
+                             uint32_t seed, uint32_t first_frame, void* cuda_stream) {
+    int rc = check_geometry(ctx, width, height, stride, n_frames, frame_pitch, 0);
+    if (rc) return rc;
+    if (!d_out) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "null device pointer");
+    if (n_frames == 0) return NV12EQ_OK;
+    if (n_frames > 65535) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "at most 65535 frames per call");
+    DeviceGuard guard(ctx->device);
+    dim3 grid(ctx->sm_count * 4, n_frames);
+    synth_nv12_kernel<<<grid, kThreads, 0, pick_stream(ctx, cuda_stream)>>>(d_out, frame_pitch, width, height, stride, seed, first_frame);
+    ctx->ctr.kernel_launches++;
+    CK(ctx, cudaGetLastError());
+    return NV12EQ_OK;
+}
+
+int nv12eq_synth_bgr_device(nv12eq_ctx* ctx, uint8_t* d_out, int n_frames, size_t frame_pitch, int width, int height, int stride,
+                            uint32_t first_frame, void* cuda_stream) {
+    int rc = check_color(ctx, width, height, stride, 0);
+    if (rc) return rc;
+    if (!d_out || n_frames < 0 || n_frames > 65535) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (n_frames == 0) return NV12EQ_OK;
+    DeviceGuard guard(ctx->device);
+    dim3 grid(ctx->sm_count * 4, n_frames);
+    synth_bgr_kernel<<<grid, kThreads, 0, pick_stream(ctx, cuda_stream)>>>(d_out, frame_pitch, width, height, stride, first_frame);
+    ctx->ctr.kernel_launches++;
+    CK(ctx, cudaGetLastError());
+    return NV12EQ_OK;
+}
+
+}  // extern "C"
