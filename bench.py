@@ -33,7 +33,7 @@ SIZES = {"4k": (3840, 2160), "1080p": (1920, 1080), "720p": (1280, 720)}
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--op", default="equalize", choices=["equalize", "clahe"])
@@ -90,7 +90,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.004)
 
     def __enter__(self):
         if self._nv:

@@ -135,12 +135,19 @@ def _nbytes(buf) -> int:
     return ctypes.sizeof(buf)
 
 
+CUDA_STREAM_LEGACY = 1      # cudaStreamLegacy
+CUDA_STREAM_PER_THREAD = 2  # cudaStreamPerThread
+
+
 def _stream_ptr(stream) -> int:
+    """None -> 0 (the context's own stream).  A torch.cuda.Stream whose handle is 0 is the legacy default stream; the
+    C-ABI reserves NULL for 'own stream', so it is passed as cudaStreamLegacy."""
     if stream is None:
         return 0
     if isinstance(stream, int):
         return stream
-    return int(stream.cuda_stream)  # torch.cuda.Stream
+    h = int(stream.cuda_stream)  # torch.cuda.Stream
+    return h if h != 0 else CUDA_STREAM_LEGACY
 
 
 class PinnedBuffer:
