@@ -103,15 +103,19 @@ __device__ __forceinline__ void clahe_tile_lut_warp(const uint32_t* __restrict__
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-// One pixel of the blend; e = {L11|L12<<16, L21|L22<<16} as bf16 pairs.
-__device__ __forceinline__ uint32_t clahe_blend(uint2 e, float xa, float xa1, float ya, float ya1) {
+// One pixel of the blend; e = {L11|L12<<16, L21|L22<<16} as bf16 pairs.  Returns the float whose LOW BYTE is the
+// result: res is a convex-ish combination of values in [0,255], so 0 <= res < 255.5 (the weights sum to 1 within a
+// few ulp); adding 1.5*2^23 performs cvRound's round-half-to-even in the FADD and leaves the integer 0..255 in the
+// low mantissa byte -- saturate_cast is the identity here, so no clamp instructions are needed.
+__device__ __forceinline__ uint32_t clahe_blend_bits(uint2 e, float xa, float xa1, float ya, float ya1) {
     const float top = __fadd_rn(__fmul_rn(bf16_lo(e.x), xa1), __fmul_rn(bf16_hi(e.x), xa));
     const float bot = __fadd_rn(__fmul_rn(bf16_lo(e.y), xa1), __fmul_rn(bf16_hi(e.y), xa));
     const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-    // cvRound + saturate: res is a convex-ish combination of values in [0,255] so 0 <= res < 255.5; adding
-    // 1.5*2^23 rounds half-to-even in the FADD and leaves the integer in the low mantissa bits.
-    const uint32_t r = __float_as_uint(__fadd_rn(res, 12582912.0f)) & 0x1ffu;
-    return min(r, 255u);
+    return __float_as_uint(__fadd_rn(res, 12582912.0f));
+}
+// low bytes of four words -> one packed word (3 PRMT)
+__device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
 __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float& a1) {
@@ -120,11 +124,14 @@ __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float&
     a = __fsub_rn(f, t1);
     a1 = __fsub_rn(1.0f, a);
 }
+// keeps a value in its register: stops the compiler from re-deriving xa1 = 1 - xa inside the pixel loop
+__device__ __forceinline__ void pin_register(float& v) { asm volatile("" : "+f"(v)); }
 
-__global__ void __launch_bounds__(kThreads, 3) clahe_kernel(const ClaheParams p) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClaheParams p) {
     extern __shared__ __align__(16) uint32_t smem[];  // 32 KB: hist[256][32] for tile items, table[256][16] uint2 for cells
     __shared__ uint32_t s_bins[256];
-    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_ticket[2];
     __shared__ int s_flag;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -133,194 +140,214 @@ __global__ void __launch_bounds__(kThreads, 3) clahe_kernel(const ClaheParams p)
     const int U = p.uv_chunks;
     const int per_slot = T + I + U;
     const uint32_t total_items = (uint32_t)(p.n_frames + p.lag) * (uint32_t)per_slot;
+    const uint32_t smem_base = smem_u32(smem);
 
+    TicketQueue q{p.ticket, s_ticket, 0u, 0u};
+    q.start();
     for (;;) {
-        if (tid == 0) s_item = atomicAdd(p.ticket, 1u);
-        __syncthreads();
-        const uint32_t item = s_item;
-        __syncthreads();
+        const uint32_t item = q.current();
         if (item >= total_items) {
-            if (tid == 0 && item == total_items + gridDim.x - 1) atomicExch(p.ticket, 0u);
+            q.finish(item, total_items);
             break;
         }
+        q.prefetch();
         const int g = (int)(item / (uint32_t)per_slot);
         const int r = (int)(item % (uint32_t)per_slot);
+        const int f = g - p.lag;
 
         if (r < T) {
-            // ------------------------- tile item: histogram -> clip -> LUT -------------------------
-            if (g >= p.n_frames) continue;
-            const uint8_t* y = p.in + (unsigned long long)g * p.pitch;
-            const int tyi = r / p.tx, txi = r - tyi * p.tx;
-            const int x0 = txi * p.tw, y0 = tyi * p.th;
-            const LaneTable hist_lane{reinterpret_cast<char*>(smem), (uint32_t)lane * 4u};
-            lane_table_zero(smem);
-            __syncthreads();
-            const bool vec_ok = !p.padded && (p.tw & 15) == 0 && (p.stride & 15) == 0 &&
-                                (((uintptr_t)y + (uintptr_t)x0) & 15) == 0 && (p.tw >> 4) <= kThreads;
-            if (vec_ok) {
-                // threads form a (rows_per_pass x vectors_per_row) grid over the tile
-                const int vpr = p.tw >> 4;
-                const int rpp = kThreads / vpr;
-                const int tr = tid / vpr, tc = tid - tr * vpr;
-                if (tr < rpp) {
-                    const uint8_t* col = y + (size_t)y0 * p.stride + x0 + tc * 16;
-                    int row = tr;
-                    for (; row + 3 * rpp < p.th; row += 4 * rpp) {
-                        int4 v0 = ld_keep(reinterpret_cast<const int4*>(col + (size_t)row * p.stride));
-                        int4 v1 = ld_keep(reinterpret_cast<const int4*>(col + (size_t)(row + rpp) * p.stride));
-                        int4 v2 = ld_keep(reinterpret_cast<const int4*>(col + (size_t)(row + 2 * rpp) * p.stride));
-                        int4 v3 = ld_keep(reinterpret_cast<const int4*>(col + (size_t)(row + 3 * rpp) * p.stride));
-                        hist_vec(v0, hist_lane); hist_vec(v1, hist_lane); hist_vec(v2, hist_lane); hist_vec(v3, hist_lane);
+            if (g < p.n_frames) {
+                // ------------------------- tile item: histogram -> clip -> LUT -------------------------
+                const uint8_t* y = p.in + (unsigned long long)g * p.pitch;
+                const int tyi = r / p.tx, txi = r - tyi * p.tx;
+                const int x0 = txi * p.tw, y0 = tyi * p.th;
+                const uint32_t lane_base = smem_base + lane * 4;
+                lane_table_zero(smem);
+                __syncthreads();
+                const bool vec_ok = !p.padded && (p.tw & 15) == 0 && (p.stride & 15) == 0 &&
+                                    (((uintptr_t)y + (uintptr_t)x0) & 15) == 0 && (p.tw >> 4) <= kThreads;
+                if (vec_ok) {
+                    // threads form a (rows_per_pass x vectors_per_row) grid over the tile; loads are software pipelined
+                    const int vpr = p.tw >> 4;
+                    const int rpp = kThreads / vpr;
+                    const int tr = tid / vpr, tc = tid - tr * vpr;
+                    if (tr < rpp) {
+                        const uint8_t* col = y + (size_t)y0 * p.stride + x0 + tc * 16;
+                        const size_t rstep = (size_t)rpp * p.stride;
+                        int row = tr;
+                        const uint8_t* ptr = col + (size_t)row * p.stride;
+                        bool have = row + rpp < p.th;  // a full round of 2 rows
+                        int4 c0, c1;
+                        if (have) {
+                            c0 = ld_keep(reinterpret_cast<const int4*>(ptr));
+                            c1 = ld_keep(reinterpret_cast<const int4*>(ptr + rstep));
+                        }
+                        while (have) {
+                            const int rn = row + 2 * rpp;
+                            const uint8_t* pn = ptr + 2 * rstep;
+                            const bool more = rn + rpp < p.th;
+                            int4 n0, n1;
+                            if (more) {
+                                n0 = ld_keep(reinterpret_cast<const int4*>(pn));
+                                n1 = ld_keep(reinterpret_cast<const int4*>(pn + rstep));
+                            }
+                            hist_vec(c0, lane_base);
+                            hist_vec(c1, lane_base);
+                            if (more) { c0 = n0; c1 = n1; }
+                            row = rn; ptr = pn; have = more;
+                        }
+                        for (; row < p.th; row += rpp, ptr += rstep) hist_vec(ld_keep(reinterpret_cast<const int4*>(ptr)), lane_base);
                     }
-                    for (; row < p.th; row += rpp)
-                        hist_vec(ld_keep(reinterpret_cast<const int4*>(col + (size_t)row * p.stride)), hist_lane);
+                } else {
+                    // general path: one warp per tile row, byte spans inside the image, reflected reads outside
+                    for (int row = warp; row < p.th; row += kWarps) {
+                        const uint8_t* src_row = y + (size_t)reflect101(y0 + row, p.h) * p.stride;
+                        const int xin = min(x0 + p.tw, p.w);  // end of the in-image part
+                        if (x0 < xin) hist_span<2>(src_row + x0, (size_t)(xin - x0), lane, 32, lane_base);
+                        for (int x = max(x0, p.w) + lane; x < x0 + p.tw; x += 32)
+                            hist_byte(src_row[reflect101(x, p.w)], lane_base);
+                    }
                 }
-            } else {
-                // general path: one warp per tile row, byte spans inside the image, reflected reads outside
-                for (int row = warp; row < p.th; row += kWarps) {
-                    const uint8_t* src_row = y + (size_t)reflect101(y0 + row, p.h) * p.stride;
-                    const int xin = min(x0 + p.tw, p.w);  // end of the in-image part
-                    if (x0 < xin) hist_span<2>(src_row + x0, (size_t)(xin - x0), lane, 32, hist_lane);
-                    for (int x = max(x0, p.w) + lane; x < x0 + p.tw; x += 32)
-                        hist_byte(src_row[reflect101(x, p.w)], hist_lane);
+                __syncthreads();
+                s_bins[tid] = lane_table_row_sum(smem, tid);
+                __syncthreads();
+                if (warp == 0) {
+                    clahe_tile_lut_warp(s_bins, p.clip_limit, p.lut_scale, p.luts + ((size_t)g * T + r) * 256, lane);
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(p.tiles_done + g, 1u);
                 }
             }
-            __syncthreads();
-            s_bins[tid] = lane_table_row_sum(smem, tid);
-            __syncthreads();
-            if (warp == 0) {
-                clahe_tile_lut_warp(s_bins, p.clip_limit, p.lut_scale, p.luts + ((size_t)g * T + r) * 256, lane);
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(p.tiles_done + g, 1u);
-            }
-            __syncthreads();
-            continue;
-        }
-
-        const int f = g - p.lag;
-        if (f < 0) continue;
-        const uint8_t* src = p.in + (unsigned long long)f * p.pitch;
-        uint8_t* dst = p.out + (unsigned long long)f * p.pitch;
-
-        if (r < T + I) {
-            // ------------------------- cell item: blend four tile LUTs -------------------------
-            if (tid == 0) {
-                bool ok = spin_until_ge(p.tiles_done + f, (uint32_t)T);
-                if (!ok) atomicExch(p.status, 1u);
-                s_flag = ok;
-            }
-            __syncthreads();
-            if (!s_flag) break;
-            const int ci = r - T;
-            const int cy = ci / p.nxc, cx = ci - cy * p.nxc;
-            const int4 xc = p.xcells[cx], yc = p.ycells[cy];
-            // pack the four LUTs: table[v][rep] (uint2), 16 replicas so a half-warp 8-byte gather is conflict-free
-            {
-                const uint8_t* L = p.luts + (size_t)f * T * 256;
-                const int v = tid;
-                const uint32_t l11 = L[(size_t)(yc.z * p.tx + xc.z) * 256 + v];
-                const uint32_t l12 = L[(size_t)(yc.z * p.tx + xc.w) * 256 + v];
-                const uint32_t l21 = L[(size_t)(yc.w * p.tx + xc.z) * 256 + v];
-                const uint32_t l22 = L[(size_t)(yc.w * p.tx + xc.w) * 256 + v];
-                uint2 e;
-                e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l12) & 0xffff0000u);
-                e.y = (__float_as_uint((float)l21) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
-                uint2* row = reinterpret_cast<uint2*>(smem) + v * 16;
+        } else if (f >= 0) {
+            const uint8_t* src = p.in + (unsigned long long)f * p.pitch;
+            uint8_t* dst = p.out + (unsigned long long)f * p.pitch;
+            if (r < T + I) {
+                // ------------------------- cell item: blend four tile LUTs -------------------------
+                if (tid == 0) {
+                    bool ok = true;
+                    if (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
+                        const long long t0 = clock64();
+                        unsigned ns = 64;
+                        while (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
+                            __nanosleep(ns);
+                            if (ns < 2048) ns <<= 1;
+                            if (clock64() - t0 > kSpinCycles) { ok = false; break; }
+                        }
+                    }
+                    if (!ok) atomicExch(p.status, 1u);
+                    s_flag = ok;
+                }
+                __syncthreads();
+                if (!s_flag) break;
+                const int ci = r - T;
+                const int cy = ci / p.nxc, cx = ci - cy * p.nxc;
+                const int4 xc = p.xcells[cx], yc = p.ycells[cy];
+                // pack the four LUTs: table[v][rep] (uint2), 16 replicas so a half-warp 8-byte gather is conflict-free
+                {
+                    const uint8_t* L = p.luts + (size_t)f * T * 256;
+                    const int v = tid;
+                    const uint32_t l11 = __ldcg(L + (size_t)(yc.z * p.tx + xc.z) * 256 + v);
+                    const uint32_t l12 = __ldcg(L + (size_t)(yc.z * p.tx + xc.w) * 256 + v);
+                    const uint32_t l21 = __ldcg(L + (size_t)(yc.w * p.tx + xc.z) * 256 + v);
+                    const uint32_t l22 = __ldcg(L + (size_t)(yc.w * p.tx + xc.w) * 256 + v);
+                    uint2 e;
+                    e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l12) & 0xffff0000u);
+                    e.y = (__float_as_uint((float)l21) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
+                    uint2* row = reinterpret_cast<uint2*>(smem) + v * 16;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) row[(j + v) & 15] = e;
-            }
-            __syncthreads();
-            char* const table_base = reinterpret_cast<char*>(smem);
-            const uint32_t rep8 = (uint32_t)(lane & 15) * 8u;
-            const int cw = xc.y - xc.x;                 // cell width in pixels
-            const int gpr = (cw + 7) >> 3;              // 8-pixel groups per row
-            const bool fast = ((xc.x & 7) == 0) && ((p.stride & 7) == 0) && ((((uintptr_t)src | (uintptr_t)dst) & 7) == 0) &&
-                              gpr <= kThreads;
-            if (fast) {
-                const int rpp = kThreads / gpr;
-                const int tr = tid / gpr, tc = tid - tr * gpr;
-                const int xg = xc.x + tc * 8;
-                if (tr < rpp) {
-                    const int npx = min(8, xc.y - xg);  // < 8 only in the last group of a ragged cell
-                    float xa[8], xa1[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) axis_weight(xg + k, p.inv_tw, xa[k], xa1[k]);
-                    int yrow = yc.x + tr;
-                    uint2 cur = make_uint2(0, 0);
-                    if (yrow < yc.y) cur = __ldcs(reinterpret_cast<const uint2*>(src + (size_t)yrow * p.stride + xg));
-                    for (; yrow < yc.y; yrow += rpp) {
-                        const int ynext = yrow + rpp;
-                        uint2 nxt = make_uint2(0, 0);
-                        if (ynext < yc.y) nxt = __ldcs(reinterpret_cast<const uint2*>(src + (size_t)ynext * p.stride + xg));
-                        float ya, ya1;
-                        axis_weight(yrow, p.inv_th, ya, ya1);
-                        uint32_t o[8];
+                    for (int j = 0; j < 16; ++j) row[(j + v) & 15] = e;
+                }
+                __syncthreads();
+                const uint32_t rep_base = smem_base + (uint32_t)(lane & 15) * 8u;
+                const int cw = xc.y - xc.x;                 // cell width in pixels
+                const int gpr = (cw + 7) >> 3;              // 8-pixel groups per row
+                const bool fast = ((xc.x & 7) == 0) && ((p.stride & 7) == 0) && ((((uintptr_t)src | (uintptr_t)dst) & 7) == 0) &&
+                                  gpr <= kThreads;
+                if (fast) {
+                    const int rpp = kThreads / gpr;
+                    const int tr = tid / gpr, tc = tid - tr * gpr;
+                    const int xg = xc.x + tc * 8;
+                    if (tr < rpp) {
+                        const int npx = min(8, xc.y - xg);  // < 8 only in the last group of a ragged cell
+                        float xa[8], xa1[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            const uint32_t wsrc = k < 4 ? cur.x : cur.y;
-                            const int kk = k & 3;
-                            const uint32_t off = kk == 0 ? ((wsrc << 7) & 0x7f80u)
-                                               : kk == 1 ? ((wsrc >> 1) & 0x7f80u)
-                                               : kk == 2 ? ((wsrc >> 9) & 0x7f80u) : ((wsrc >> 17) & 0x7f80u);
-                            o[k] = clahe_blend(*reinterpret_cast<const uint2*>(table_base + (off | rep8)), xa[k], xa1[k], ya, ya1);
+                            axis_weight(xg + k, p.inv_tw, xa[k], xa1[k]);
+                            pin_register(xa1[k]);
                         }
-                        uint8_t* drow = dst + (size_t)yrow * p.stride + xg;
-                        if (npx == 8) {
-                            uint2 ov;
-                            ov.x = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-                            ov.y = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
-                            __stcs(reinterpret_cast<uint2*>(drow), ov);
-                        } else {
+                        int yrow = yc.x + tr;
+                        const size_t rstep = (size_t)rpp * p.stride;
+                        const uint8_t* sp = src + (size_t)yrow * p.stride + xg;
+                        uint8_t* dp = dst + (size_t)yrow * p.stride + xg;
+                        uint2 cur = make_uint2(0, 0);
+                        if (yrow < yc.y) cur = __ldcs(reinterpret_cast<const uint2*>(sp));
+                        for (; yrow < yc.y; yrow += rpp, sp += rstep, dp += rstep) {
+                            uint2 nxt = make_uint2(0, 0);
+                            if (yrow + rpp < yc.y) nxt = __ldcs(reinterpret_cast<const uint2*>(sp + rstep));
+                            float ya, ya1;
+                            axis_weight(yrow, p.inv_th, ya, ya1);
+                            uint32_t o[8];
+                            o[0] = clahe_blend_bits(lds_u64(rep_base + (byte_of<0>(cur.x) << 7)), xa[0], xa1[0], ya, ya1);
+                            o[1] = clahe_blend_bits(lds_u64(rep_base + (byte_of<1>(cur.x) << 7)), xa[1], xa1[1], ya, ya1);
+                            o[2] = clahe_blend_bits(lds_u64(rep_base + (byte_of<2>(cur.x) << 7)), xa[2], xa1[2], ya, ya1);
+                            o[3] = clahe_blend_bits(lds_u64(rep_base + (byte_of<3>(cur.x) << 7)), xa[3], xa1[3], ya, ya1);
+                            o[4] = clahe_blend_bits(lds_u64(rep_base + (byte_of<0>(cur.y) << 7)), xa[4], xa1[4], ya, ya1);
+                            o[5] = clahe_blend_bits(lds_u64(rep_base + (byte_of<1>(cur.y) << 7)), xa[5], xa1[5], ya, ya1);
+                            o[6] = clahe_blend_bits(lds_u64(rep_base + (byte_of<2>(cur.y) << 7)), xa[6], xa1[6], ya, ya1);
+                            o[7] = clahe_blend_bits(lds_u64(rep_base + (byte_of<3>(cur.y) << 7)), xa[7], xa1[7], ya, ya1);
+                            if (npx == 8) {
+                                __stcs(reinterpret_cast<uint2*>(dp),
+                                       make_uint2(pack_low_bytes(o[0], o[1], o[2], o[3]), pack_low_bytes(o[4], o[5], o[6], o[7])));
+                            } else {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                if (k < npx) drow[k] = (uint8_t)o[k];
+                                for (int k = 0; k < 8; ++k)
+                                    if (k < npx) dp[k] = (uint8_t)o[k];
+                            }
+                            cur = nxt;
                         }
-                        cur = nxt;
+                    }
+                } else {
+                    // general path: one pixel per thread per step
+                    const int ch = yc.y - yc.x;
+                    const long long npix = (long long)cw * ch;
+                    for (long long i = tid; i < npix; i += kThreads) {
+                        const int ry = (int)(i / cw), rx = (int)(i - (long long)ry * cw);
+                        const int x = xc.x + rx, yy = yc.x + ry;
+                        float xa, xa1, ya, ya1;
+                        axis_weight(x, p.inv_tw, xa, xa1);
+                        axis_weight(yy, p.inv_th, ya, ya1);
+                        const uint32_t v = src[(size_t)yy * p.stride + x];
+                        dst[(size_t)yy * p.stride + x] = (uint8_t)clahe_blend_bits(lds_u64(rep_base + (v << 7)), xa, xa1, ya, ya1);
                     }
                 }
             } else {
-                // general path: one pixel per thread per step
-                const int ch = yc.y - yc.x;
-                const long long npix = (long long)cw * ch;
-                for (long long i = tid; i < npix; i += kThreads) {
-                    const int ry = (int)(i / cw), rx = (int)(i - (long long)ry * cw);
-                    const int x = xc.x + rx, yy = yc.x + ry;
-                    float xa, xa1, ya, ya1;
-                    axis_weight(x, p.inv_tw, xa, xa1);
-                    axis_weight(yy, p.inv_th, ya, ya1);
-                    const uint32_t v = src[(size_t)yy * p.stride + x];
-                    dst[(size_t)yy * p.stride + x] =
-                        (uint8_t)clahe_blend(*reinterpret_cast<const uint2*>(table_base + ((v << 7) | rep8)), xa, xa1, ya, ya1);
+                // ------------------------- uv item -------------------------
+                const int c = r - T - I;
+                const bool copy_uv = p.uv_mode == UV_COPY && src != dst;
+                const size_t uv_off = (size_t)p.stride * p.h;
+                if (p.flat) {
+                    const unsigned long long b0 = min((unsigned long long)c * p.uv_chunk, p.uv_bytes);
+                    const unsigned long long b1 = min(b0 + p.uv_chunk, p.uv_bytes);
+                    if (copy_uv) copy_span<2>(src + uv_off + b0, dst + uv_off + b0, (size_t)(b1 - b0), tid, kThreads);
+                    else if (p.uv_mode == UV_GRAY128) fill_span(dst + uv_off + b0, (size_t)(b1 - b0), tid, kThreads, 128);
+                } else {
+                    const int rows = p.h / 2;
+                    const int r0 = min(c * p.uv_rows_chunk, rows), r1 = min(r0 + p.uv_rows_chunk, rows);
+                    for (int row = r0 + warp; row < r1; row += kWarps) {
+                        const size_t off = uv_off + (size_t)row * p.stride;
+                        if (copy_uv) copy_span<2>(src + off, dst + off, (size_t)p.w, lane, 32);
+                        else if (p.uv_mode == UV_GRAY128) fill_span(dst + off, (size_t)p.w, lane, 32, 128);
+                    }
                 }
             }
-        } else {
-            // ------------------------- uv item -------------------------
-            const int c = r - T - I;
-            const bool copy_uv = p.uv_mode == UV_COPY && src != dst;
-            const size_t uv_off = (size_t)p.stride * p.h;
-            if (p.flat) {
-                const unsigned long long b0 = min((unsigned long long)c * p.uv_chunk, p.uv_bytes);
-                const unsigned long long b1 = min(b0 + p.uv_chunk, p.uv_bytes);
-                if (copy_uv) copy_span<4>(src + uv_off + b0, dst + uv_off + b0, (size_t)(b1 - b0), tid, kThreads);
-                else if (p.uv_mode == UV_GRAY128) fill_span(dst + uv_off + b0, (size_t)(b1 - b0), tid, kThreads, 128);
-            } else {
-                const int rows = p.h / 2;
-                const int r0 = min(c * p.uv_rows_chunk, rows), r1 = min(r0 + p.uv_rows_chunk, rows);
-                for (int row = r0 + warp; row < r1; row += kWarps) {
-                    const size_t off = uv_off + (size_t)row * p.stride;
-                    if (copy_uv) copy_span<2>(src + off, dst + off, (size_t)p.w, lane, 32);
-                    else if (p.uv_mode == UV_GRAY128) fill_span(dst + off, (size_t)p.w, lane, 32, 128);
-                }
+            // Every apply-side item of frame f has passed its tiles_done wait once it gets here; the last one to
+            // check in returns the counters to zero for the next launch (the LUT storage needs no cleaning).
+            if (tid == 0 && atomicAdd(p.applied + f, 1u) == (uint32_t)(I + U - 1)) {
+                p.tiles_done[f] = 0;
+                p.applied[f] = 0;
             }
         }
-        // the last apply-side item of the frame returns the workspace to its zero state
-        __syncthreads();
-        if (tid == 0 && atomicAdd(p.applied + f, 1u) == (uint32_t)(I + U - 1)) {
-            p.tiles_done[f] = 0;
-            p.applied[f] = 0;
-        }
-        __syncthreads();
+        q.advance();
     }
 }
 

@@ -6,9 +6,12 @@
 //     whole Y plane is one contiguous byte span, cut into 16-byte vectors).
 //   * 256-bin histograms are accumulated in shared memory as hist[bin][lane] (uint32, 32 KB): lane L of every
 //     warp only ever touches column L, so a warp-wide shared atomic hits 32 distinct banks regardless of the
-//     pixel values -- no bank conflicts, no same-address serialisation, for flat patches and noise alike.
+//     pixel values -- no bank conflicts, no same-address serialisation, for flat patches and noise alike
+//     (ncu: 1.1 shared wavefronts per ATOMS, the same cost as a conflict-free load).
 //   * Look-up tables are expanded in shared memory as table[value][lane] (uint32, byte-replicated, 32 KB) for the
 //     same reason: the gather `table[pixel][lane]` is conflict-free for arbitrary pixel values.
+//   * One CTA works on one item at a time and an item needs only one of the two tables, so they share the same
+//     32 KB of dynamic shared memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,10 +26,8 @@ constexpr int kLaneTableBytes = kLaneTableWords * 4;
 enum : int { UV_COPY = 0, UV_GRAY128 = 1, UV_SKIP = 2 };
 
 // ---- memory access helpers -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-// no-return shared atomic increment on a 32-bit shared address
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// no-return shared atomic increment on a 32-bit shared address (SASS: ATOMS.POPC.INC)
 __device__ __forceinline__ void red_shared_inc(uint32_t saddr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr) : "memory");
 }
@@ -51,143 +52,148 @@ __device__ __forceinline__ int4 ld_keep(const int4* p) { return __ldg(p); }
 __device__ __forceinline__ int4 ld_stream(const int4* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(int4* p, int4 v) { __stcs(p, v); }
 
+// Byte k of a packed word, zero extended (one PRMT).
+template <int K>
+__device__ __forceinline__ uint32_t byte_of(uint32_t w) { return __byte_perm(w, 0u, 0x4440u + K); }
+
 // ---- byte-span walkers ----------------------------------------------------------------------------------
 // A span is n contiguous bytes.  `tid`/`nthr` select the participating threads (a whole CTA for flat planes, one
 // warp for one row of a strided plane).  Unaligned heads/tails are handled with byte accesses.
 struct SpanSplit {
-    size_t head;  // bytes before the first 16-byte aligned address
-    size_t nvec;  // number of 16-byte vectors
-    size_t tail0; // offset of the first tail byte
+    uint32_t head;  // bytes before the first 16-byte aligned address
+    uint32_t nvec;  // number of 16-byte vectors (a span is one chunk or one row: far below 2^32 vectors)
+    size_t tail0;   // offset of the first tail byte
 };
 __device__ __forceinline__ SpanSplit split_span(const void* p, size_t n) {
     SpanSplit s;
-    size_t mis = (size_t)((16 - ((uintptr_t)p & 15)) & 15);
-    s.head = mis < n ? mis : n;
-    s.nvec = (n - s.head) >> 4;
-    s.tail0 = s.head + (s.nvec << 4);
+    const size_t mis = (size_t)((16 - ((uintptr_t)p & 15)) & 15);
+    s.head = (uint32_t)(mis < n ? mis : n);
+    s.nvec = (uint32_t)((n - s.head) >> 4);
+    s.tail0 = (size_t)s.head + ((size_t)s.nvec << 4);
     return s;
 }
 
-// A lane-private table is addressed as base + ((value << 7) | lane4): `base` is a CTA-uniform pointer into shared
-// memory (ends up in a uniform register: ATOMS/LDS [R + UR]), lane4 = lane * 4.  Extracting byte k of a packed
-// word, scaling it by 128 and OR-ing in the lane offset is one shift plus one LOP3 per pixel.
-struct LaneTable {
-    char* base;       // CTA-uniform, points into shared memory
-    uint32_t lane4;   // (threadIdx.x & 31) * 4
-};
-__device__ __forceinline__ uint32_t* lt_ptr(const LaneTable& t, uint32_t scaled_value) {
-    return reinterpret_cast<uint32_t*>(t.base + (scaled_value | t.lane4));
-}
-__device__ __forceinline__ void hist_byte(uint32_t v, const LaneTable& t) { atomicAdd(lt_ptr(t, v << 7), 1u); }
-__device__ __forceinline__ void hist_word(uint32_t w, const LaneTable& t) {
-    atomicAdd(lt_ptr(t, (w << 7) & 0x7f80u), 1u);
-    atomicAdd(lt_ptr(t, (w >> 1) & 0x7f80u), 1u);
-    atomicAdd(lt_ptr(t, (w >> 9) & 0x7f80u), 1u);
-    atomicAdd(lt_ptr(t, (w >> 17) & 0x7f80u), 1u);
-}
-__device__ __forceinline__ void hist_vec(int4 v, const LaneTable& t) {
-    hist_word((uint32_t)v.x, t);
-    hist_word((uint32_t)v.y, t);
-    hist_word((uint32_t)v.z, t);
-    hist_word((uint32_t)v.w, t);
+// Software-pipelined walk over nvec 16-byte vectors: the loads of round r+1 are issued before round r is consumed,
+// so every thread always has U vector loads in flight while it works (ncu showed the unpipelined loop stalled on
+// long_scoreboard for a third of its samples).
+template <int U, class Load, class Use>
+__device__ __forceinline__ void pipelined_vectors(uint32_t nvec, int tid, int nthr, Load load, Use use) {
+    const uint32_t step = (uint32_t)nthr * U;
+    uint32_t i = tid;
+    // rounds in which all U vectors of this thread are in range
+    uint32_t rounds = (i + step - nthr < nvec) ? (nvec - (i + step - nthr) + step - 1) / step : 0u;
+    int4 cur[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) cur[u] = make_int4(0, 0, 0, 0);
+    if (rounds) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = load(i + (uint32_t)u * nthr);
+    }
+    for (; rounds; --rounds) {
+        int4 nxt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) nxt[u] = make_int4(0, 0, 0, 0);
+        if (rounds > 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) nxt[u] = load(i + step + (uint32_t)u * nthr);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) use(i + (uint32_t)u * nthr, cur[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+        i += step;
+    }
+    for (; i < nvec; i += nthr) use(i, load(i));
 }
 
-template <int UNROLL>
-__device__ __forceinline__ void hist_span(const uint8_t* __restrict__ p, size_t n, int tid, int nthr,
-                                          const LaneTable& hist) {
-    SpanSplit s = split_span(p, n);
-    for (size_t i = tid; i < s.head; i += nthr) hist_byte(p[i], hist);
+// A lane-private table lives at 32-bit shared address `lane_base` (= table base + lane*4); the entry of value v
+// is at lane_base + v*128.  Per pixel: one PRMT (byte extract), one shift-add, one shared access.
+__device__ __forceinline__ void hist_byte(uint32_t v, uint32_t lane_base) { red_shared_inc(lane_base + (v << 7)); }
+__device__ __forceinline__ void hist_word(uint32_t w, uint32_t lane_base) {
+    red_shared_inc(lane_base + (byte_of<0>(w) << 7));
+    red_shared_inc(lane_base + (byte_of<1>(w) << 7));
+    red_shared_inc(lane_base + (byte_of<2>(w) << 7));
+    red_shared_inc(lane_base + (byte_of<3>(w) << 7));
+}
+__device__ __forceinline__ void hist_vec(int4 v, uint32_t lane_base) {
+    hist_word((uint32_t)v.x, lane_base);
+    hist_word((uint32_t)v.y, lane_base);
+    hist_word((uint32_t)v.z, lane_base);
+    hist_word((uint32_t)v.w, lane_base);
+}
+
+template <int U>
+__device__ __forceinline__ void hist_span(const uint8_t* __restrict__ p, size_t n, int tid, int nthr, uint32_t lane_base) {
+    const SpanSplit s = split_span(p, n);
+    for (uint32_t i = tid; i < s.head; i += nthr) hist_byte(p[i], lane_base);
     const int4* v = reinterpret_cast<const int4*>(p + s.head);
-    size_t i = tid;
-    const size_t step = (size_t)nthr * UNROLL;
-    for (; i + step - nthr < s.nvec; i += step) {
-        int4 r[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) r[u] = ld_keep(v + i + (size_t)u * nthr);
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) hist_vec(r[u], hist);
-    }
-    for (; i < s.nvec; i += nthr) hist_vec(ld_keep(v + i), hist);
-    for (size_t j = s.tail0 + tid; j < n; j += nthr) hist_byte(p[j], hist);
+    pipelined_vectors<U>(
+        s.nvec, tid, nthr, [&](uint32_t i) { return ld_keep(v + i); }, [&](uint32_t, int4 x) { hist_vec(x, lane_base); });
+    for (size_t j = s.tail0 + tid; j < n; j += nthr) hist_byte(p[j], lane_base);
 }
 
 // Gather through a byte-replicated lane table (entries are lut * 0x01010101).
-__device__ __forceinline__ uint32_t lut_word(uint32_t w, const LaneTable& t) {
-    const uint32_t a = *lt_ptr(t, (w << 7) & 0x7f80u);
-    const uint32_t b = *lt_ptr(t, (w >> 1) & 0x7f80u);
-    const uint32_t c = *lt_ptr(t, (w >> 9) & 0x7f80u);
-    const uint32_t d = *lt_ptr(t, (w >> 17) & 0x7f80u);
+__device__ __forceinline__ uint32_t lut_word(uint32_t w, uint32_t lane_base) {
+    const uint32_t a = lds_u32(lane_base + (byte_of<0>(w) << 7));
+    const uint32_t b = lds_u32(lane_base + (byte_of<1>(w) << 7));
+    const uint32_t c = lds_u32(lane_base + (byte_of<2>(w) << 7));
+    const uint32_t d = lds_u32(lane_base + (byte_of<3>(w) << 7));
     const uint32_t lo = __byte_perm(a, b, 0x5140);  // a.b0, b.b0 in the low half (all bytes of a, b are equal)
     const uint32_t hi = __byte_perm(c, d, 0x5140);
     return __byte_perm(lo, hi, 0x5410);
 }
-__device__ __forceinline__ int4 lut_vec(int4 v, const LaneTable& t) {
+__device__ __forceinline__ int4 lut_vec(int4 v, uint32_t lane_base) {
     int4 o;
-    o.x = (int)lut_word((uint32_t)v.x, t);
-    o.y = (int)lut_word((uint32_t)v.y, t);
-    o.z = (int)lut_word((uint32_t)v.z, t);
-    o.w = (int)lut_word((uint32_t)v.w, t);
+    o.x = (int)lut_word((uint32_t)v.x, lane_base);
+    o.y = (int)lut_word((uint32_t)v.y, lane_base);
+    o.z = (int)lut_word((uint32_t)v.z, lane_base);
+    o.w = (int)lut_word((uint32_t)v.w, lane_base);
     return o;
 }
-__device__ __forceinline__ uint8_t lut_byte(uint8_t v, const LaneTable& t) { return (uint8_t)*lt_ptr(t, (uint32_t)v << 7); }
+__device__ __forceinline__ uint8_t lut_byte(uint8_t v, uint32_t lane_base) { return (uint8_t)lds_u32(lane_base + ((uint32_t)v << 7)); }
 
 // dst[i] = table[src[i]] over a span.  src and dst must be congruent mod 16 for the vector path; otherwise the
 // whole span goes through the byte path (correct, slow, only hit by exotic pointer/pitch combinations).
-template <int UNROLL>
+template <int U>
 __device__ __forceinline__ void lut_span(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n, int tid,
-                                         int nthr, const LaneTable& table) {
+                                         int nthr, uint32_t lane_base) {
     if ((((uintptr_t)src ^ (uintptr_t)dst) & 15) != 0) {
-        for (size_t i = tid; i < n; i += nthr) dst[i] = lut_byte(src[i], table);
+        for (size_t i = tid; i < n; i += nthr) dst[i] = lut_byte(src[i], lane_base);
         return;
     }
-    SpanSplit s = split_span(src, n);
-    for (size_t i = tid; i < s.head; i += nthr) dst[i] = lut_byte(src[i], table);
+    const SpanSplit s = split_span(src, n);
+    for (uint32_t i = tid; i < s.head; i += nthr) dst[i] = lut_byte(src[i], lane_base);
     const int4* v = reinterpret_cast<const int4*>(src + s.head);
     int4* o = reinterpret_cast<int4*>(dst + s.head);
-    size_t i = tid;
-    const size_t step = (size_t)nthr * UNROLL;
-    for (; i + step - nthr < s.nvec; i += step) {
-        int4 r[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) r[u] = ld_stream(v + i + (size_t)u * nthr);
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) st_stream(o + i + (size_t)u * nthr, lut_vec(r[u], table));
-    }
-    for (; i < s.nvec; i += nthr) st_stream(o + i, lut_vec(ld_stream(v + i), table));
-    for (size_t j = s.tail0 + tid; j < n; j += nthr) dst[j] = lut_byte(src[j], table);
+    pipelined_vectors<U>(
+        s.nvec, tid, nthr, [&](uint32_t i) { return ld_stream(v + i); },
+        [&](uint32_t i, int4 x) { st_stream(o + i, lut_vec(x, lane_base)); });
+    for (size_t j = s.tail0 + tid; j < n; j += nthr) dst[j] = lut_byte(src[j], lane_base);
 }
 
-template <int UNROLL>
+template <int U>
 __device__ __forceinline__ void copy_span(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n, int tid,
                                           int nthr) {
     if ((((uintptr_t)src ^ (uintptr_t)dst) & 15) != 0) {
         for (size_t i = tid; i < n; i += nthr) dst[i] = src[i];
         return;
     }
-    SpanSplit s = split_span(src, n);
-    for (size_t i = tid; i < s.head; i += nthr) dst[i] = src[i];
+    const SpanSplit s = split_span(src, n);
+    for (uint32_t i = tid; i < s.head; i += nthr) dst[i] = src[i];
     const int4* v = reinterpret_cast<const int4*>(src + s.head);
     int4* o = reinterpret_cast<int4*>(dst + s.head);
-    size_t i = tid;
-    const size_t step = (size_t)nthr * UNROLL;
-    for (; i + step - nthr < s.nvec; i += step) {
-        int4 r[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) r[u] = ld_stream(v + i + (size_t)u * nthr);
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) st_stream(o + i + (size_t)u * nthr, r[u]);
-    }
-    for (; i < s.nvec; i += nthr) st_stream(o + i, ld_stream(v + i));
+    pipelined_vectors<U>(
+        s.nvec, tid, nthr, [&](uint32_t i) { return ld_stream(v + i); }, [&](uint32_t i, int4 x) { st_stream(o + i, x); });
     for (size_t j = s.tail0 + tid; j < n; j += nthr) dst[j] = src[j];
 }
 
 __device__ __forceinline__ void fill_span(uint8_t* __restrict__ dst, size_t n, int tid, int nthr, uint8_t value) {
-    SpanSplit s = split_span(dst, n);
-    for (size_t i = tid; i < s.head; i += nthr) dst[i] = value;
+    const SpanSplit s = split_span(dst, n);
+    for (uint32_t i = tid; i < s.head; i += nthr) dst[i] = value;
     int4* o = reinterpret_cast<int4*>(dst + s.head);
     const int w = (int)(value * 0x01010101u);
     const int4 vv = make_int4(w, w, w, w);
-    for (size_t i = tid; i < s.nvec; i += nthr) st_stream(o + i, vv);
+    for (uint32_t i = tid; i < s.nvec; i += nthr) st_stream(o + i, vv);
     for (size_t j = s.tail0 + tid; j < n; j += nthr) dst[j] = value;
 }
 
@@ -243,19 +249,36 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t k) {
     return k;
 }
 
-// Bounded spin on a global counter (thread 0 only); returns false on timeout (~2 s) so a logic error can never
-// hang the GPU.  Progress is guaranteed by construction: the counter is only waited on by CTAs whose work ticket
-// is larger than the tickets of all CTAs that feed it, and those are resident or finished.
-__device__ __forceinline__ bool spin_until_ge(const uint32_t* ctr, uint32_t target) {
-    if (ld_acquire_u32(ctr) >= target) return true;
-    const long long t0 = clock64();
-    unsigned ns = 32;
-    while (ld_acquire_u32(ctr) < target) {
-        __nanosleep(ns);
-        if (ns < 1024) ns <<= 1;
-        if (clock64() - t0 > (4ll << 30)) return false;
+// Spin budget for dependency waits (~2 s): a logic error can never hang the GPU.  Progress is guaranteed by
+// construction: an item only waits on items with smaller tickets, and those are resident or finished.
+constexpr long long kSpinCycles = 4ll << 30;
+
+// Work tickets.  Thread 0 draws the NEXT ticket at the start of an item and publishes it at the end, so the
+// global-atomic round trip is hidden behind the item's work.  Every CTA draws exactly one ticket >= total; the
+// CTA that draws the last of those resets the counter for the next launch.
+struct TicketQueue {
+    uint32_t* counter;
+    uint32_t* slots;  // shared uint32[2]
+    uint32_t pending;
+    uint32_t round;
+    __device__ __forceinline__ void start() {
+        round = 0;
+        if (threadIdx.x == 0) slots[0] = atomicAdd(counter, 1u);
+        __syncthreads();
     }
-    return true;
-}
+    __device__ __forceinline__ uint32_t current() const { return slots[round & 1]; }
+    __device__ __forceinline__ void prefetch() {
+        if (threadIdx.x == 0) pending = atomicAdd(counter, 1u);
+    }
+    // also the end-of-item barrier that protects the shared tables of the next item
+    __device__ __forceinline__ void advance() {
+        if (threadIdx.x == 0) slots[(round + 1) & 1] = pending;
+        ++round;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void finish(uint32_t item, uint32_t total) {
+        if (threadIdx.x == 0 && item == total + gridDim.x - 1) atomicExch(counter, 0u);
+    }
+};
 
 }  // namespace nv12eq

@@ -6,8 +6,8 @@
 // Schedule ("ticket-lag"): work is cut into items drawn by CTAs from a global ticket counter, so items START
 // strictly in ticket order.  Slot g of the ticket space holds 2C items:
 //     r <  C : histogram chunk r of frame g           (if g < n_frames) -> smem hist[256][32] -> global hist[g][256]
-//     r >= C : LUT + apply + UV of chunk r-C of frame g - lag (if >= 0);  waits until all C histogram chunks of
-//              that frame have been added (done[f] == C)
+//     r >= C : LUT + apply + UV of chunk r-C of frame g - lag (if >= 0);  waits until the global histogram of
+//              that frame adds up to W*H pixels (the histogram is its own completion flag)
 // A waiting CTA can only wait on items with smaller tickets, which are resident or finished, so the wait always
 // ends (any lag >= 0, any grid size).  With lag >= 1 a frame's histogram is complete before its apply items are
 // drawn, the Y plane it just streamed through is still in the 126 MB L2 when it is read the second time, and
@@ -39,14 +39,16 @@ struct EqParams {
     int y_rows_chunk, uv_rows_chunk;           // strided: rows per chunk
     long long total_px;                        // pixel count the histogram describes (W*H unless spatially split)
     uint32_t* hist;     // [n_frames][256], zero on entry; self-cleaned unless PH_EXTERNAL_HIST
-    uint32_t* done;     // [n_frames] histogram chunks added; self-cleaned
-    uint32_t* applied;  // [n_frames] apply chunks finished; self-cleaned
+    uint32_t* applied;  // [n_frames] apply items that have read the histogram; self-cleaned
     uint32_t* ticket;   // [1] work counter; self-cleaned
     uint32_t* status;   // [1] sticky error word (spin timeout)
 };
 
 // One warp: 256-bin histogram (global) -> equalization LUT (shared), SURVEY.md A.1 / oracle_equalize_lut.
-__device__ __forceinline__ void equalize_lut_warp(const uint32_t* __restrict__ ghist, long long total,
+// Returns false when the histogram does not (yet) add up to `expect` pixels.  The histogram itself is the completion
+// signal: it starts at zero, every pixel is added exactly once with an L2 atomic, so sum == expect means every
+// chunk of the frame has been added and the values are final -- no fence, no flag, no extra round trip.
+__device__ __forceinline__ bool equalize_lut_warp(const uint32_t* __restrict__ ghist, long long total, long long expect,
                                                   uint8_t* __restrict__ slut, int lane) {
     uint32_t h[8];
     const uint4* g4 = reinterpret_cast<const uint4*>(ghist) + lane * 2;
@@ -60,11 +62,12 @@ __device__ __forceinline__ void equalize_lut_warp(const uint32_t* __restrict__ g
         if (h[j] != 0) first = j;
     }
     const uint32_t nz = __ballot_sync(0xffffffffu, first < 8);
-    uint32_t incl = warp_incl_scan(lsum, lane);
+    const uint32_t incl = warp_incl_scan(lsum, lane);
+    if (expect >= 0 && (long long)__shfl_sync(0xffffffffu, incl, 31) != expect) return false;
     if (nz == 0) {  // empty plane: nothing will be read from the LUT
 #pragma unroll
         for (int j = 0; j < 8; ++j) slut[lane * 8 + j] = 0;
-        return;
+        return true;
     }
     const int l0 = __ffs(nz) - 1;
     const int j0 = __shfl_sync(0xffffffffu, first, l0);
@@ -85,7 +88,7 @@ __device__ __forceinline__ void equalize_lut_warp(const uint32_t* __restrict__ g
     if ((long long)h_i0 == total) {  // constant image: dst = i0 everywhere
 #pragma unroll
         for (int j = 0; j < 8; ++j) slut[lane * 8 + j] = (uint8_t)i0;
-        return;
+        return true;
     }
     const float scale = __fdiv_rn(255.0f, (float)(total - (long long)h_i0));
 #pragma unroll
@@ -96,6 +99,7 @@ __device__ __forceinline__ void equalize_lut_warp(const uint32_t* __restrict__ g
         if (i > i0) v = round_sat_u8(__fmul_rn(__uint2float_rn(run - cum_i0), scale));
         slut[i] = (uint8_t)v;
     }
+    return true;
 }
 
 // Chunk c of a plane of `rows` rows.  Flat planes are cut by bytes, strided planes by rows.
@@ -118,117 +122,121 @@ __device__ __forceinline__ PlaneChunk plane_chunk(int flat, int c, unsigned long
     return pc;
 }
 
-__global__ void __launch_bounds__(kThreads, 3) equalize_kernel(const EqParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t* s_hist = smem;                     // [256][32]
-    uint32_t* s_table = smem + kLaneTableWords;  // [256][32]
+// Chroma rows of chunk c: passthrough copy or neutral grey, by threads [tid0, tid0 + nthr) of the CTA.
+__device__ __forceinline__ void equalize_uv_chunk(const EqParams& p, const uint8_t* src, uint8_t* dst, int c, int tid,
+                                                  int nthr) {
+    const bool copy_uv = p.uv_mode == UV_COPY && src != dst;
+    if (!(copy_uv || p.uv_mode == UV_GRAY128) || tid < 0) return;
+    const size_t uv_off = (size_t)p.stride * p.h;
+    const PlaneChunk uc = plane_chunk(p.flat, c, p.uv_bytes, p.uv_chunk, p.h / 2, p.uv_rows_chunk);
+    if (p.flat) {
+        const size_t n = (size_t)(uc.b1 - uc.b0);
+        if (copy_uv) copy_span<2>(src + uv_off + uc.b0, dst + uv_off + uc.b0, n, tid, nthr);
+        else fill_span(dst + uv_off + uc.b0, n, tid, nthr, 128);
+    } else {
+        const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+        for (int r = uc.r0 + w; r < uc.r1; r += nw) {
+            const size_t off = uv_off + (size_t)r * p.stride;
+            if (copy_uv) copy_span<2>(src + off, dst + off, (size_t)p.w, lane, 32);
+            else fill_span(dst + off, (size_t)p.w, lane, 32, 128);
+        }
+    }
+}
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqParams p) {
+    extern __shared__ __align__(16) uint32_t smem[];  // 32 KB: hist[256][32] (histogram items) or table[256][32] (apply items)
     __shared__ __align__(16) uint8_t s_lut[256];
-    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_ticket[2];
     __shared__ int s_flag;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const LaneTable hist_lane{reinterpret_cast<char*>(s_hist), (uint32_t)lane * 4u};
-    const LaneTable table_lane{reinterpret_cast<char*>(s_table), (uint32_t)lane * 4u};
+    const uint32_t lane_base = smem_u32(smem) + lane * 4;
     const int C = p.chunks;
     const bool do_hist = (p.phases & PH_HIST) != 0, do_apply = (p.phases & PH_APPLY) != 0;
     const bool external = (p.phases & PH_EXTERNAL_HIST) != 0;
     const int lag = (do_hist && do_apply) ? p.lag : 0;
     const uint32_t total_items = (uint32_t)(p.n_frames + lag) * (uint32_t)(2 * C);
 
+    TicketQueue q{p.ticket, s_ticket, 0u, 0u};
+    q.start();
     for (;;) {
-        if (tid == 0) s_item = atomicAdd(p.ticket, 1u);
-        __syncthreads();
-        const uint32_t item = s_item;
-        __syncthreads();
+        const uint32_t item = q.current();
         if (item >= total_items) {
-            // every CTA fails exactly once; the last failure resets the counter for the next launch
-            if (tid == 0 && item == total_items + gridDim.x - 1) atomicExch(p.ticket, 0u);
+            q.finish(item, total_items);
             break;
         }
+        q.prefetch();
         const int g = (int)(item / (uint32_t)(2 * C));
         const int r2 = (int)(item % (uint32_t)(2 * C));
         const bool hist_item = r2 < C;
         const int c = hist_item ? r2 : r2 - C;
+        const int f = g - lag;
 
-        // ---------------- histogram of chunk c of frame g ----------------
         if (hist_item && do_hist && g < p.n_frames) {
+            // ---------------- histogram of chunk c of frame g ----------------
             const uint8_t* y = p.in + (unsigned long long)g * p.pitch;
-            lane_table_zero(s_hist);
+            lane_table_zero(smem);
             __syncthreads();
             const PlaneChunk pc = plane_chunk(p.flat, c, p.y_bytes, p.y_chunk, p.h, p.y_rows_chunk);
             if (p.flat) {
-                hist_span<4>(y + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, hist_lane);
+                hist_span<2>(y + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, lane_base);
             } else {
                 for (int r = pc.r0 + warp; r < pc.r1; r += kWarps)
-                    hist_span<2>(y + (size_t)r * p.stride, (size_t)p.w, lane, 32, hist_lane);
+                    hist_span<2>(y + (size_t)r * p.stride, (size_t)p.w, lane, 32, lane_base);
             }
             __syncthreads();
-            const uint32_t cnt = lane_table_row_sum(s_hist, tid);
+            const uint32_t cnt = lane_table_row_sum(smem, tid);
             if (cnt) atomicAdd(p.hist + (size_t)g * 256 + tid, cnt);
-            if (!external) {
-                __threadfence();
-                __syncthreads();
-                if (tid == 0) atomicAdd(p.done + g, 1u);
-            } else {
-                __syncthreads();
-            }
-        }
-
-        // ---------------- LUT + apply + UV for chunk c of frame f ----------------
-        const int f = g - lag;
-        if (!hist_item && do_apply && f >= 0) {
-            if (!external) {
-                if (tid == 0) {
-                    bool ok = spin_until_ge(p.done + f, (uint32_t)C);
-                    if (!ok) atomicExch(p.status, 1u);
-                    s_flag = ok;
-                }
-                __syncthreads();
-                if (!s_flag) break;
-            }
-            if (warp == 0) equalize_lut_warp(p.hist + (size_t)f * 256, p.total_px, s_lut, lane);
-            __syncthreads();
-            lane_table_fill_from_lut(s_table, s_lut);
-            __syncthreads();
-
+        } else if (!hist_item && do_apply && f >= 0) {
+            // ---------------- LUT + apply + UV for chunk c of frame f ----------------
             const uint8_t* src = p.in + (unsigned long long)f * p.pitch;
             uint8_t* dst = p.out + (unsigned long long)f * p.pitch;
-            const PlaneChunk pc = plane_chunk(p.flat, c, p.y_bytes, p.y_chunk, p.h, p.y_rows_chunk);
-            if (p.flat) {
-                lut_span<4>(src + pc.b0, dst + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, table_lane);
-            } else {
-                for (int r = pc.r0 + warp; r < pc.r1; r += kWarps)
-                    lut_span<2>(src + (size_t)r * p.stride, dst + (size_t)r * p.stride, (size_t)p.w, lane, 32, table_lane);
-            }
-            // chroma rows
-            const bool copy_uv = p.uv_mode == UV_COPY && src != dst;
-            if (copy_uv || p.uv_mode == UV_GRAY128) {
-                const size_t uv_off = (size_t)p.stride * p.h;
-                const PlaneChunk uc = plane_chunk(p.flat, c, p.uv_bytes, p.uv_chunk, p.h / 2, p.uv_rows_chunk);
-                if (p.flat) {
-                    const size_t n = (size_t)(uc.b1 - uc.b0);
-                    if (copy_uv) copy_span<4>(src + uv_off + uc.b0, dst + uv_off + uc.b0, n, tid, kThreads);
-                    else fill_span(dst + uv_off + uc.b0, n, tid, kThreads, 128);
-                } else {
-                    for (int r = uc.r0 + warp; r < uc.r1; r += kWarps) {
-                        const size_t off = uv_off + (size_t)r * p.stride;
-                        if (copy_uv) copy_span<2>(src + off, dst + off, (size_t)p.w, lane, 32);
-                        else fill_span(dst + off, (size_t)p.w, lane, 32, 128);
+            if (warp == 0) {
+                // wait for the complete histogram of frame f and build its LUT; the other warps move chroma meanwhile
+                uint32_t* gh = p.hist + (size_t)f * 256;
+                const long long expect = external ? -1ll : p.total_px;
+                bool ok = equalize_lut_warp(gh, p.total_px, expect, s_lut, lane);
+                if (!ok) {
+                    const long long t0 = clock64();
+                    unsigned ns = 64;
+                    while (!(ok = equalize_lut_warp(gh, p.total_px, expect, s_lut, lane))) {
+                        __nanosleep(ns);
+                        if (ns < 2048) ns <<= 1;
+                        if (clock64() - t0 > kSpinCycles) break;
                     }
                 }
-            }
-            if (!external) {
-                // last apply chunk of the frame returns the workspace to its zero state
-                __syncthreads();
-                if (tid == 0) s_flag = (atomicAdd(p.applied + f, 1u) == (uint32_t)(C - 1));
-                __syncthreads();
-                if (s_flag) {
-                    p.hist[(size_t)f * 256 + tid] = 0;
-                    if (tid == 0) { p.done[f] = 0; p.applied[f] = 0; }
+                if (lane == 0) {
+                    s_flag = ok;
+                    if (!ok) atomicExch(p.status, 1u);
                 }
+                if (ok && !external) {
+                    // every apply item reads the histogram once; the last reader returns it to its zero state
+                    uint32_t last = 0;
+                    if (lane == 0) last = (atomicAdd(p.applied + f, 1u) == (uint32_t)(C - 1));
+                    if (__shfl_sync(0xffffffffu, last, 0)) {
+                        uint4* g4 = reinterpret_cast<uint4*>(gh) + lane * 2;
+                        g4[0] = make_uint4(0, 0, 0, 0);
+                        g4[1] = make_uint4(0, 0, 0, 0);
+                        if (lane == 0) p.applied[f] = 0;
+                    }
+                }
+            } else {
+                equalize_uv_chunk(p, src, dst, c, tid - 32, kThreads - 32);
             }
             __syncthreads();
+            if (!s_flag) break;  // dependency wait timed out (cannot happen; see kSpinCycles)
+            lane_table_fill_from_lut(smem, s_lut);
+            __syncthreads();
+            const PlaneChunk pc = plane_chunk(p.flat, c, p.y_bytes, p.y_chunk, p.h, p.y_rows_chunk);
+            if (p.flat) {
+                lut_span<2>(src + pc.b0, dst + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, lane_base);
+            } else {
+                for (int r = pc.r0 + warp; r < pc.r1; r += kWarps)
+                    lut_span<2>(src + (size_t)r * p.stride, dst + (size_t)r * p.stride, (size_t)p.w, lane, 32, lane_base);
+            }
         }
+        q.advance();
     }
 }
 

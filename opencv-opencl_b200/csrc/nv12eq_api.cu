@@ -176,8 +176,11 @@ uint32_t* ws_status(Workspace& w) { return reinterpret_cast<uint32_t*>(w.misc.p)
 
 int ensure_attrs(nv12eq_ctx* ctx) {
     if (ctx->attrs_set) return NV12EQ_OK;
-    CK(ctx, cudaFuncSetAttribute(equalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kLaneTableBytes));
-    CK(ctx, cudaFuncSetAttribute(clahe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(equalize_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(equalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(equalize_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(clahe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(clahe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     ctx->attrs_set = true;
     return NV12EQ_OK;
 }
@@ -219,8 +222,9 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
     p.uv_bytes = (unsigned long long)w * (h / 2);
     p.total_px = total_px ? total_px : (long long)w * h;
 
+    const int per_sm = ctx->tune_ctas > 0 ? ctx->tune_ctas : 4;
     // chunks per frame: ~128 KB of luma per item, but never fewer items than ~2 waves of CTAs
-    const int ctas = ctx->sm_count * (ctx->tune_ctas > 0 ? ctx->tune_ctas : 3);
+    const int ctas = ctx->sm_count * (ctx->tune_ctas > 0 ? ctx->tune_ctas : 4);
     long long C = (long long)((p.y_bytes + 131071) / 131072);
     if (ctx->tune_chunks > 0) C = ctx->tune_chunks;
     else if ((long long)n * C < 2ll * ctas) C = std::min<long long>((2ll * ctas + n - 1) / n, (long long)((p.y_bytes + 16383) / 16384));
@@ -232,22 +236,33 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
     p.uv_chunk = std::max<unsigned long long>(4096, round4k((p.uv_bytes + C - 1) / C));
     p.y_rows_chunk = (int)((h + C - 1) / C);
     p.uv_rows_chunk = (int)((h / 2 + C - 1) / C);
-    p.lag = ctx->tune_lag > 0 ? ctx->tune_lag : 2;
-    if (ctx->tune_lag < 0) p.lag = 0;
-    p.lag = std::min(p.lag, std::max(n - 1, 0));
+    // Frame lag between a frame's histogram items and its apply items.  An item drawn with ticket t finishes when
+    // the counter is near t + grid (every resident CTA finishes about one item per item time), so the histogram
+    // items of a frame are done once grid more tickets have been drawn: lag >= grid / items_per_slot (+1 margin).
+    // The Y planes of `lag` frames have to stay in L2 for the second read: cap the footprint at ~64 MB.
+    {
+        const long long grid_ctas = (long long)ctx->sm_count * per_sm;
+        long long lag = (grid_ctas + 2 * C - 1) / (2 * C) + 1;
+        const long long cap = std::max<long long>(1, (64ll << 20) / (long long)std::max<unsigned long long>(1, p.y_bytes));
+        lag = std::min(lag, cap);
+        if (ctx->tune_lag > 0) lag = ctx->tune_lag;
+        if (ctx->tune_lag < 0) lag = 0;
+        p.lag = (int)std::min<long long>(lag, std::max(n - 1, 0));
+    }
     p.hist = ext_hist ? ext_hist : reinterpret_cast<uint32_t*>(ws.hist.p);
-    p.done = ws_counter(ws, 0);
     p.applied = ws_counter(ws, 1);
     p.ticket = ws_ticket(ws);
     p.status = ws_status(ws);
 
-    const size_t smem = 2 * kLaneTableBytes;
+    const size_t smem = kLaneTableBytes;
     auto go = [&](int phases) -> int {
         p.phases = phases;
         const bool both = (phases & PH_HIST) && (phases & PH_APPLY);
         long long items = (long long)(n + (both ? p.lag : 0)) * 2 * C;
-        int grid = grid_for(ctx, items, 3);
-        equalize_kernel<<<grid, kThreads, smem, st>>>(p);
+        int grid = grid_for(ctx, items, 4);
+        if (per_sm <= 3) equalize_kernel<3><<<grid, kThreads, smem, st>>>(p);
+        else if (per_sm == 4) equalize_kernel<4><<<grid, kThreads, smem, st>>>(p);
+        else equalize_kernel<5><<<grid, kThreads, smem, st>>>(p);
         ctx->ctr.kernel_launches++;
         CK(ctx, cudaGetLastError());
         return NV12EQ_OK;
@@ -363,7 +378,7 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
         p.uv_rows_chunk = (h / 2 + U - 1) / U;
     }
     p.uv_chunks = U;
-    p.lag = ctx->tune_lag > 0 ? ctx->tune_lag : 1;
+    p.lag = ctx->tune_lag > 0 ? ctx->tune_lag : 4;
     if (ctx->tune_lag < 0) p.lag = 0;
     p.lag = std::min(p.lag, std::max(n - 1, 0));
     p.luts = reinterpret_cast<uint8_t*>(ws.luts.p);
@@ -375,8 +390,10 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     const long long per_slot = (long long)T + (long long)p.nxc * p.nyc + U;
     const long long items = (long long)(n + p.lag) * per_slot;
     if (items >= (1ll << 32)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "too many work items");
+    const int per_sm = ctx->tune_ctas > 0 ? ctx->tune_ctas : 3;
     const int grid = grid_for(ctx, items, 3);
-    clahe_kernel<<<grid, kThreads, kLaneTableBytes, st>>>(p);
+    if (per_sm <= 3) clahe_kernel<3><<<grid, kThreads, kLaneTableBytes, st>>>(p);
+    else clahe_kernel<4><<<grid, kThreads, kLaneTableBytes, st>>>(p);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
     return NV12EQ_OK;
