@@ -22,7 +22,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnv12eq.so")
+LIB_PATH = os.environ.get("NV12EQ_LIB") or os.path.join(_HERE, "libnv12eq.so")  # NV12EQ_LIB: experimental builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nv12eq.h")
 
 # enums of include/nv12eq.h
@@ -49,6 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ into libnv12eq.so for sm_100a with nvcc (in-tree, so the .so travels with the repo)."""
     csrc = os.path.join(_HERE, "csrc")
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))] + [HEADER_PATH]
+    if os.environ.get("NV12EQ_LIB"):
+        return LIB_PATH  # an explicitly selected experimental build is used as is
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
         out = subprocess.run(["make", "-C", csrc] + (["-B"] if force else []), capture_output=True, text=True)

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                     }
                 }
                 __syncthreads();
-                s_bins[tid] = lane_table_row_sum(smem, tid);
+                if (tid < 256) s_bins[tid] = lane_table_row_sum(smem, tid);
                 __syncthreads();
                 if (warp == 0) {
                     clahe_tile_lut_warp(s_bins, p.clip_limit, p.lut_scale, p.luts + ((size_t)g * T + r) * 256, lane);
@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 const int4 xc = p.xcells[cx], yc = p.ycells[cy];
                 // pack the four LUTs: table[v][rep] (uint2), 16 replicas so a half-warp 8-byte gather is conflict-free
                 {
+                    constexpr int kShare = kThreads / 256, kPer = 16 / kShare;
                     const uint8_t* L = p.luts + (size_t)f * T * 256;
-                    const int v = tid;
+                    const int v = tid & 255, part = tid >> 8;
                     const uint32_t l11 = __ldcg(L + (size_t)(yc.z * p.tx + xc.z) * 256 + v);
                     const uint32_t l12 = __ldcg(L + (size_t)(yc.z * p.tx + xc.w) * 256 + v);
                     const uint32_t l21 = __ldcg(L + (size_t)(yc.w * p.tx + xc.z) * 256 + v);
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                     e.y = (__float_as_uint((float)l21) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
                     uint2* row = reinterpret_cast<uint2*>(smem) + v * 16;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) row[(j + v) & 15] = e;
+                    for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & 15] = e;
                 }
                 __syncthreads();
                 const uint32_t rep_base = smem_base + (uint32_t)(lane & 15) * 8u;

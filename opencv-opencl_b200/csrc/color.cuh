@@ -10,6 +10,7 @@
 
 namespace nv12eq {
 
+constexpr int kColorThreads = 256;
 enum : int { COLOR_YUV = 0, COLOR_YCRCB = 1 };
 
 __device__ __forceinline__ int descale14(int v) { return (v + 8192) >> 14; }
@@ -50,7 +51,7 @@ struct ColorParams {
 };
 
 // 4 pixels per thread: 12 BGR bytes (three 32-bit words) -> 4 luma bytes (one word).
-__global__ void __launch_bounds__(kThreads) bgr_to_luma_kernel(const ColorParams p) {
+__global__ void __launch_bounds__(kColorThreads) bgr_to_luma_kernel(const ColorParams p) {
     const int f = blockIdx.y;
     const uint8_t* src = p.bgr_in + (unsigned long long)f * p.bgr_pitch;
     uint8_t* dst = p.y_plane + (size_t)f * p.w * p.h;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kThreads) bgr_to_luma_kernel(const ColorParams
         const long long nquad = npx >> 2;
         const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
         uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-        for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += (long long)gridDim.x * kThreads) {
+        for (long long q = (long long)blockIdx.x * kColorThreads + threadIdx.x; q < nquad; q += (long long)gridDim.x * kColorThreads) {
             const uint32_t a = __ldg(s32 + 3 * q), b = __ldg(s32 + 3 * q + 1), c = __ldg(s32 + 3 * q + 2);
             const int y0 = bgr_luma(a & 255, (a >> 8) & 255, (a >> 16) & 255);
             const int y1 = bgr_luma(a >> 24, b & 255, (b >> 8) & 255);
@@ -68,11 +69,11 @@ __global__ void __launch_bounds__(kThreads) bgr_to_luma_kernel(const ColorParams
             const int y3 = bgr_luma((c >> 8) & 255, (c >> 16) & 255, c >> 24);
             d32[q] = (uint32_t)y0 | ((uint32_t)y1 << 8) | ((uint32_t)y2 << 16) | ((uint32_t)y3 << 24);
         }
-        for (long long i = (nquad << 2) + (long long)blockIdx.x * kThreads + threadIdx.x; i < npx;
-             i += (long long)gridDim.x * kThreads)
+        for (long long i = (nquad << 2) + (long long)blockIdx.x * kColorThreads + threadIdx.x; i < npx;
+             i += (long long)gridDim.x * kColorThreads)
             dst[i] = (uint8_t)bgr_luma(src[3 * i], src[3 * i + 1], src[3 * i + 2]);
     } else {
-        for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < npx; i += (long long)gridDim.x * kThreads) {
+        for (long long i = (long long)blockIdx.x * kColorThreads + threadIdx.x; i < npx; i += (long long)gridDim.x * kColorThreads) {
             const int r = (int)(i / p.w), c = (int)(i - (long long)r * p.w);
             const uint8_t* px = src + (size_t)r * p.stride + 3 * (size_t)c;
             dst[i] = (uint8_t)bgr_luma(px[0], px[1], px[2]);
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kThreads) bgr_to_luma_kernel(const ColorParams
     }
 }
 
-__global__ void __launch_bounds__(kThreads) bgr_recombine_kernel(const ColorParams p) {
+__global__ void __launch_bounds__(kColorThreads) bgr_recombine_kernel(const ColorParams p) {
     const int f = blockIdx.y;
     const uint8_t* src = p.bgr_in + (unsigned long long)f * p.bgr_pitch;
     uint8_t* dst = p.bgr_out + (unsigned long long)f * p.bgr_pitch;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) bgr_recombine_kernel(const ColorPara
         const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
         const uint32_t* y32 = reinterpret_cast<const uint32_t*>(y2p);
         uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-        for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += (long long)gridDim.x * kThreads) {
+        for (long long q = (long long)blockIdx.x * kColorThreads + threadIdx.x; q < nquad; q += (long long)gridDim.x * kColorThreads) {
             const uint32_t a = __ldcs(s32 + 3 * q), b = __ldcs(s32 + 3 * q + 1), c = __ldcs(s32 + 3 * q + 2);
             const uint32_t yy = __ldcs(y32 + q);
             const uint32_t p0 = bgr_recombine(a & 255, (a >> 8) & 255, (a >> 16) & 255, yy & 255, p.mode);
@@ -103,13 +104,13 @@ __global__ void __launch_bounds__(kThreads) bgr_recombine_kernel(const ColorPara
             __stcs(d32 + 3 * q + 1, (p1 >> 8) | (p2 << 16));
             __stcs(d32 + 3 * q + 2, (p2 >> 16) | (p3 << 8));
         }
-        for (long long i = (nquad << 2) + (long long)blockIdx.x * kThreads + threadIdx.x; i < npx;
-             i += (long long)gridDim.x * kThreads) {
+        for (long long i = (nquad << 2) + (long long)blockIdx.x * kColorThreads + threadIdx.x; i < npx;
+             i += (long long)gridDim.x * kColorThreads) {
             const uint32_t o = bgr_recombine(src[3 * i], src[3 * i + 1], src[3 * i + 2], y2p[i], p.mode);
             dst[3 * i] = (uint8_t)o; dst[3 * i + 1] = (uint8_t)(o >> 8); dst[3 * i + 2] = (uint8_t)(o >> 16);
         }
     } else {
-        for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < npx; i += (long long)gridDim.x * kThreads) {
+        for (long long i = (long long)blockIdx.x * kColorThreads + threadIdx.x; i < npx; i += (long long)gridDim.x * kColorThreads) {
             const int r = (int)(i / p.w), c = (int)(i - (long long)r * p.w);
             const uint8_t* px = src + (size_t)r * p.stride + 3 * (size_t)c;
             uint8_t* o8 = dst + (size_t)r * p.stride + 3 * (size_t)c;

@@ -18,7 +18,7 @@
 
 namespace nv12eq {
 
-constexpr int kThreads = 256;            // threads per CTA for every kernel here
+constexpr int kThreads = 512;            // threads per CTA of the hot kernels (2 CTAs/SM: 32 warps, 64 registers/thread)
 constexpr int kWarps = kThreads / 32;
 constexpr int kLaneTableWords = 256 * 32; // one [256][32] uint32 table
 constexpr int kLaneTableBytes = kLaneTableWords * 4;
@@ -205,8 +205,8 @@ __device__ __forceinline__ void lane_table_zero(uint32_t* tab) {
 #pragma unroll
     for (int i = 0; i < kLaneTableWords / 4 / kThreads; ++i) t4[threadIdx.x + i * kThreads] = z;
 }
-// Sum row `bin` (32 lane columns) of a [256][32] table.  Rotated 16-byte reads keep the 8 threads of a
-// quarter-warp phase on 8 different bank groups.
+// Sum row `bin` (32 lane columns) of a [256][32] table (call with bin = tid for tid < 256).  Rotated 16-byte reads
+// keep the 8 threads of a quarter-warp phase on 8 different bank groups.
 __device__ __forceinline__ uint32_t lane_table_row_sum(const uint32_t* tab, int bin) {
     const uint4* row = reinterpret_cast<const uint4*>(tab + bin * 32);
     uint32_t s = 0;
@@ -217,14 +217,15 @@ __device__ __forceinline__ uint32_t lane_table_row_sum(const uint32_t* tab, int 
     }
     return s;
 }
-// Expand a 256-byte LUT (shared memory) into table[v][lane] = lut[v] * 0x01010101.
+// Expand a 256-byte LUT (shared memory) into table[v][lane] = lut[v] * 0x01010101.  kThreads / 256 threads share a row.
 __device__ __forceinline__ void lane_table_fill_from_lut(uint32_t* tab, const uint8_t* lut256) {
-    const int v = threadIdx.x;  // kThreads == 256
+    constexpr int kShare = kThreads / 256, kPer = 8 / kShare;
+    const int v = threadIdx.x & 255, part = threadIdx.x >> 8;
     const uint32_t w = (uint32_t)lut256[v] * 0x01010101u;
     uint4* row = reinterpret_cast<uint4*>(tab + v * 32);
     const uint4 q = make_uint4(w, w, w, w);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) row[(j + v) & 7] = q;
+    for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & 7] = q;
 }
 
 // ---- warp scan ------------------------------------------------------------------------------------------

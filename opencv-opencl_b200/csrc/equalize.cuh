@@ -186,8 +186,10 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
                     hist_span<2>(y + (size_t)r * p.stride, (size_t)p.w, lane, 32, lane_base);
             }
             __syncthreads();
-            const uint32_t cnt = lane_table_row_sum(smem, tid);
-            if (cnt) atomicAdd(p.hist + (size_t)g * 256 + tid, cnt);
+            if (tid < 256) {
+                const uint32_t cnt = lane_table_row_sum(smem, tid);
+                if (cnt) atomicAdd(p.hist + (size_t)g * 256 + tid, cnt);
+            }
         } else if (!hist_item && do_apply && f >= 0) {
             // ---------------- LUT + apply + UV for chunk c of frame f ----------------
             const uint8_t* src = p.in + (unsigned long long)f * p.pitch;
@@ -241,7 +243,8 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
 }
 
 // ---- Appendix B synthetic frames, generated on the device (bench / test utility) -------------------------
-__global__ void __launch_bounds__(kThreads) synth_nv12_kernel(uint8_t* out, unsigned long long pitch, int w, int h,
+constexpr int kSynthThreads = 256;
+__global__ void __launch_bounds__(kSynthThreads) synth_nv12_kernel(uint8_t* out, unsigned long long pitch, int w, int h,
                                                               int stride, uint32_t seed, uint32_t first_frame) {
     const int f = blockIdx.y;
     uint8_t* base = out + (unsigned long long)f * pitch;
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kThreads) synth_nv12_kernel(uint8_t* out, unsi
     const int rows = h + h / 2;
     const int bw = max(w / 16, 1), bh = max(h / 9, 1);
     const long long total = (long long)rows * w;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    for (long long i = (long long)blockIdx.x * kSynthThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kSynthThreads) {
         const int r = (int)(i / w), c = (int)(i - (long long)r * w);
         uint8_t v;
         if (r < h) {
@@ -268,14 +271,14 @@ __global__ void __launch_bounds__(kThreads) synth_nv12_kernel(uint8_t* out, unsi
     }
 }
 
-__global__ void __launch_bounds__(kThreads) synth_bgr_kernel(uint8_t* out, unsigned long long pitch, int w, int h,
+__global__ void __launch_bounds__(kSynthThreads) synth_bgr_kernel(uint8_t* out, unsigned long long pitch, int w, int h,
                                                              int stride, uint32_t first_frame) {
     const int f = blockIdx.y;
     uint8_t* base = out + (unsigned long long)f * pitch;
     const uint32_t frame = first_frame + (uint32_t)f;
     const int bw = max(w / 16, 1), bh = max(h / 9, 1);
     const long long total = (long long)h * w * 3;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    for (long long i = (long long)blockIdx.x * kSynthThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kSynthThreads) {
         const long long px = i / 3;
         const int ch = (int)(i - px * 3);
         const int r = (int)(px / w), c = (int)(px - (long long)r * w);

@@ -176,11 +176,11 @@ uint32_t* ws_status(Workspace& w) { return reinterpret_cast<uint32_t*>(w.misc.p)
 
 int ensure_attrs(nv12eq_ctx* ctx) {
     if (ctx->attrs_set) return NV12EQ_OK;
+    CK(ctx, cudaFuncSetAttribute(equalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
-    CK(ctx, cudaFuncSetAttribute(equalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
-    CK(ctx, cudaFuncSetAttribute(equalize_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
-    CK(ctx, cudaFuncSetAttribute(clahe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
-    CK(ctx, cudaFuncSetAttribute(clahe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(clahe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(clahe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     ctx->attrs_set = true;
     return NV12EQ_OK;
 }
@@ -222,9 +222,9 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
     p.uv_bytes = (unsigned long long)w * (h / 2);
     p.total_px = total_px ? total_px : (long long)w * h;
 
-    const int per_sm = ctx->tune_ctas > 0 ? ctx->tune_ctas : 4;
+    const int per_sm = ctx->tune_ctas > 0 ? std::min(ctx->tune_ctas, 3) : 2;
     // chunks per frame: ~128 KB of luma per item, but never fewer items than ~2 waves of CTAs
-    const int ctas = ctx->sm_count * (ctx->tune_ctas > 0 ? ctx->tune_ctas : 4);
+    const int ctas = ctx->sm_count * per_sm;
     long long C = (long long)((p.y_bytes + 131071) / 131072);
     if (ctx->tune_chunks > 0) C = ctx->tune_chunks;
     else if ((long long)n * C < 2ll * ctas) C = std::min<long long>((2ll * ctas + n - 1) / n, (long long)((p.y_bytes + 16383) / 16384));
@@ -243,7 +243,7 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
     {
         const long long grid_ctas = (long long)ctx->sm_count * per_sm;
         long long lag = (grid_ctas + 2 * C - 1) / (2 * C) + 1;
-        const long long cap = std::max<long long>(1, (64ll << 20) / (long long)std::max<unsigned long long>(1, p.y_bytes));
+        const long long cap = std::max<long long>(1, (48ll << 20) / (long long)std::max<unsigned long long>(1, p.y_bytes));
         lag = std::min(lag, cap);
         if (ctx->tune_lag > 0) lag = ctx->tune_lag;
         if (ctx->tune_lag < 0) lag = 0;
@@ -259,10 +259,10 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
         p.phases = phases;
         const bool both = (phases & PH_HIST) && (phases & PH_APPLY);
         long long items = (long long)(n + (both ? p.lag : 0)) * 2 * C;
-        int grid = grid_for(ctx, items, 4);
-        if (per_sm <= 3) equalize_kernel<3><<<grid, kThreads, smem, st>>>(p);
-        else if (per_sm == 4) equalize_kernel<4><<<grid, kThreads, smem, st>>>(p);
-        else equalize_kernel<5><<<grid, kThreads, smem, st>>>(p);
+        int grid = grid_for(ctx, items, 2);
+        if (per_sm <= 1) equalize_kernel<1><<<grid, kThreads, smem, st>>>(p);
+        else if (per_sm == 2) equalize_kernel<2><<<grid, kThreads, smem, st>>>(p);
+        else equalize_kernel<3><<<grid, kThreads, smem, st>>>(p);
         ctx->ctr.kernel_launches++;
         CK(ctx, cudaGetLastError());
         return NV12EQ_OK;
@@ -378,9 +378,6 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
         p.uv_rows_chunk = (h / 2 + U - 1) / U;
     }
     p.uv_chunks = U;
-    p.lag = ctx->tune_lag > 0 ? ctx->tune_lag : 4;
-    if (ctx->tune_lag < 0) p.lag = 0;
-    p.lag = std::min(p.lag, std::max(n - 1, 0));
     p.luts = reinterpret_cast<uint8_t*>(ws.luts.p);
     p.tiles_done = ws_counter(ws, 0);
     p.applied = ws_counter(ws, 1);
@@ -388,12 +385,22 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     p.status = ws_status(ws);
 
     const long long per_slot = (long long)T + (long long)p.nxc * p.nyc + U;
+    const int per_sm = ctx->tune_ctas > 0 ? std::min(ctx->tune_ctas, 2) : 2;
+    {
+        // same reasoning as for equalizeHist; tile items run ~1.5x longer than the average item
+        const long long grid_ctas = (long long)ctx->sm_count * per_sm;
+        long long lag = (3 * grid_ctas / 2 + per_slot - 1) / per_slot + 1;
+        const long long cap = std::max<long long>(1, (48ll << 20) / std::max<long long>(1, (long long)w * h));
+        lag = std::min(lag, cap);
+        if (ctx->tune_lag > 0) lag = ctx->tune_lag;
+        if (ctx->tune_lag < 0) lag = 0;
+        p.lag = (int)std::min<long long>(lag, std::max(n - 1, 0));
+    }
     const long long items = (long long)(n + p.lag) * per_slot;
     if (items >= (1ll << 32)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "too many work items");
-    const int per_sm = ctx->tune_ctas > 0 ? ctx->tune_ctas : 3;
-    const int grid = grid_for(ctx, items, 3);
-    if (per_sm <= 3) clahe_kernel<3><<<grid, kThreads, kLaneTableBytes, st>>>(p);
-    else clahe_kernel<4><<<grid, kThreads, kLaneTableBytes, st>>>(p);
+    const int grid = grid_for(ctx, items, 2);
+    if (per_sm <= 1) clahe_kernel<1><<<grid, kThreads, kLaneTableBytes, st>>>(p);
+    else clahe_kernel<2><<<grid, kThreads, kLaneTableBytes, st>>>(p);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
     return NV12EQ_OK;
@@ -414,16 +421,16 @@ int launch_color(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     cp.bgr_in = d_in; cp.bgr_out = d_out; cp.bgr_pitch = pitch; cp.n_frames = n;
     cp.w = w; cp.h = h; cp.stride = stride; cp.y_plane = y1; cp.y2_plane = y2; cp.mode = mode;
     const long long quads = ((long long)plane + 3) / 4;
-    const int gx = (int)std::max<long long>(1, std::min<long long>((quads + kThreads - 1) / kThreads, (long long)ctx->sm_count * 8));
+    const int gx = (int)std::max<long long>(1, std::min<long long>((quads + kColorThreads - 1) / kColorThreads, (long long)ctx->sm_count * 8));
     dim3 grid(gx, n);
-    bgr_to_luma_kernel<<<grid, kThreads, 0, st>>>(cp);
+    bgr_to_luma_kernel<<<grid, kColorThreads, 0, st>>>(cp);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
     // the luma planes are Y-only "frames" of pitch w*h: stride == w, chroma skipped
     if (use_clahe) rc = launch_clahe(ctx, ws, y1, y2, n, plane, w, h, w, clip, tx, ty, UV_SKIP, st);
     else rc = launch_equalize(ctx, ws, y1, y2, n, plane, w, h, w, UV_SKIP, st);
     if (rc) return rc;
-    bgr_recombine_kernel<<<grid, kThreads, 0, st>>>(cp);
+    bgr_recombine_kernel<<<grid, kColorThreads, 0, st>>>(cp);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
     return NV12EQ_OK;
@@ -884,7 +891,7 @@ int nv12eq_synth_nv12_device(nv12eq_ctx* ctx, uint8_t* d_out, int n_frames, size
     if (n_frames > 65535) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "at most 65535 frames per call");
     DeviceGuard guard(ctx->device);
     dim3 grid(ctx->sm_count * 4, n_frames);
-    synth_nv12_kernel<<<grid, kThreads, 0, pick_stream(ctx, cuda_stream)>>>(d_out, frame_pitch, width, height, stride, seed, first_frame);
+    synth_nv12_kernel<<<grid, kSynthThreads, 0, pick_stream(ctx, cuda_stream)>>>(d_out, frame_pitch, width, height, stride, seed, first_frame);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
     return NV12EQ_OK;
@@ -898,7 +905,7 @@ int nv12eq_synth_bgr_device(nv12eq_ctx* ctx, uint8_t* d_out, int n_frames, size_
     if (n_frames == 0) return NV12EQ_OK;
     DeviceGuard guard(ctx->device);
     dim3 grid(ctx->sm_count * 4, n_frames);
-    synth_bgr_kernel<<<grid, kThreads, 0, pick_stream(ctx, cuda_stream)>>>(d_out, frame_pitch, width, height, stride, first_frame);
+    synth_bgr_kernel<<<grid, kSynthThreads, 0, pick_stream(ctx, cuda_stream)>>>(d_out, frame_pitch, width, height, stride, first_frame);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
     return NV12EQ_OK;
