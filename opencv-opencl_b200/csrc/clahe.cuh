@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                     const int rpp = kThreads / vpr;
                     const int tr = tid / vpr, tc = tid - tr * vpr;
                     if (tr < rpp) {
+                        const uint64_t keep = l2_policy_evict_last();
                         const uint8_t* col = y + (size_t)y0 * p.stride + x0 + tc * 16;
                         const size_t rstep = (size_t)rpp * p.stride;
                         int row = tr;
@@ -179,8 +180,8 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                         bool have = row + rpp < p.th;  // a full round of 2 rows
                         int4 c0, c1;
                         if (have) {
-                            c0 = ld_keep(reinterpret_cast<const int4*>(ptr));
-                            c1 = ld_keep(reinterpret_cast<const int4*>(ptr + rstep));
+                            c0 = ldg128_hint(ptr, keep);
+                            c1 = ldg128_hint(ptr + rstep, keep);
                         }
                         while (have) {
                             const int rn = row + 2 * rpp;
@@ -188,22 +189,22 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                             const bool more = rn + rpp < p.th;
                             int4 n0, n1;
                             if (more) {
-                                n0 = ld_keep(reinterpret_cast<const int4*>(pn));
-                                n1 = ld_keep(reinterpret_cast<const int4*>(pn + rstep));
+                                n0 = ldg128_hint(pn, keep);
+                                n1 = ldg128_hint(pn + rstep, keep);
                             }
                             hist_vec(c0, lane_base);
                             hist_vec(c1, lane_base);
                             if (more) { c0 = n0; c1 = n1; }
                             row = rn; ptr = pn; have = more;
                         }
-                        for (; row < p.th; row += rpp, ptr += rstep) hist_vec(ld_keep(reinterpret_cast<const int4*>(ptr)), lane_base);
+                        for (; row < p.th; row += rpp, ptr += rstep) hist_vec(ldg128_hint(ptr, keep), lane_base);
                     }
                 } else {
                     // general path: one warp per tile row, byte spans inside the image, reflected reads outside
                     for (int row = warp; row < p.th; row += kWarps) {
                         const uint8_t* src_row = y + (size_t)reflect101(y0 + row, p.h) * p.stride;
                         const int xin = min(x0 + p.tw, p.w);  // end of the in-image part
-                        if (x0 < xin) hist_span<2>(src_row + x0, (size_t)(xin - x0), lane, 32, lane_base);
+                        if (x0 < xin) hist_span(src_row + x0, (size_t)(xin - x0), lane, 32, lane_base);
                         for (int x = max(x0, p.w) + lane; x < x0 + p.tw; x += 32)
                             hist_byte(src_row[reflect101(x, p.w)], lane_base);
                     }
@@ -276,15 +277,16 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                             axis_weight(xg + k, p.inv_tw, xa[k], xa1[k]);
                             pin_register(xa1[k]);
                         }
+                        const uint64_t once = l2_policy_evict_first();
                         int yrow = yc.x + tr;
                         const size_t rstep = (size_t)rpp * p.stride;
                         const uint8_t* sp = src + (size_t)yrow * p.stride + xg;
                         uint8_t* dp = dst + (size_t)yrow * p.stride + xg;
                         uint2 cur = make_uint2(0, 0);
-                        if (yrow < yc.y) cur = __ldcs(reinterpret_cast<const uint2*>(sp));
+                        if (yrow < yc.y) cur = ldg64_hint(sp, once);
                         for (; yrow < yc.y; yrow += rpp, sp += rstep, dp += rstep) {
                             uint2 nxt = make_uint2(0, 0);
-                            if (yrow + rpp < yc.y) nxt = __ldcs(reinterpret_cast<const uint2*>(sp + rstep));
+                            if (yrow + rpp < yc.y) nxt = ldg64_hint(sp + rstep, once);
                             float ya, ya1;
                             axis_weight(yrow, p.inv_th, ya, ya1);
                             uint32_t o[8];
@@ -297,8 +299,8 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                             o[6] = clahe_blend_bits(lds_u64(rep_base + (byte_of<2>(cur.y) << 7)), xa[6], xa1[6], ya, ya1);
                             o[7] = clahe_blend_bits(lds_u64(rep_base + (byte_of<3>(cur.y) << 7)), xa[7], xa1[7], ya, ya1);
                             if (npx == 8) {
-                                __stcs(reinterpret_cast<uint2*>(dp),
-                                       make_uint2(pack_low_bytes(o[0], o[1], o[2], o[3]), pack_low_bytes(o[4], o[5], o[6], o[7])));
+                                stg64_hint(dp, make_uint2(pack_low_bytes(o[0], o[1], o[2], o[3]), pack_low_bytes(o[4], o[5], o[6], o[7])),
+                                           once);
                             } else {
 #pragma unroll
                                 for (int k = 0; k < 8; ++k)
@@ -329,14 +331,14 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 if (p.flat) {
                     const unsigned long long b0 = min((unsigned long long)c * p.uv_chunk, p.uv_bytes);
                     const unsigned long long b1 = min(b0 + p.uv_chunk, p.uv_bytes);
-                    if (copy_uv) copy_span<2>(src + uv_off + b0, dst + uv_off + b0, (size_t)(b1 - b0), tid, kThreads);
+                    if (copy_uv) copy_span(src + uv_off + b0, dst + uv_off + b0, (size_t)(b1 - b0), tid, kThreads);
                     else if (p.uv_mode == UV_GRAY128) fill_span(dst + uv_off + b0, (size_t)(b1 - b0), tid, kThreads, 128);
                 } else {
                     const int rows = p.h / 2;
                     const int r0 = min(c * p.uv_rows_chunk, rows), r1 = min(r0 + p.uv_rows_chunk, rows);
                     for (int row = r0 + warp; row < r1; row += kWarps) {
                         const size_t off = uv_off + (size_t)row * p.stride;
-                        if (copy_uv) copy_span<2>(src + off, dst + off, (size_t)p.w, lane, 32);
+                        if (copy_uv) copy_span(src + off, dst + off, (size_t)p.w, lane, 32);
                         else if (p.uv_mode == UV_GRAY128) fill_span(dst + off, (size_t)p.w, lane, 32, 128);
                     }
                 }

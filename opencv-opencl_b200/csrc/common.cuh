@@ -46,11 +46,58 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Y plane first read: keep it in L2 (it is read again by the apply / interpolation pass).
-__device__ __forceinline__ int4 ld_keep(const int4* p) { return __ldg(p); }
-// Last read of a line / write-once output: streaming (evict-first) so it does not push the Y plane out of L2.
-__device__ __forceinline__ int4 ld_stream(const int4* p) { return __ldcs(p); }
-__device__ __forceinline__ void st_stream(int4* p, int4 v) { __stcs(p, v); }
+// L2 residency is managed explicitly (sm_100 LDG/STG carry an L2 eviction priority; SASS: LDG.E.NA.ELL2.256 etc.):
+//   first read of the Y plane  -> evict_last  : it is read again by the apply / interpolation pass a few frames later
+//   second read, chroma, output-> evict_first : streaming data must not push the Y planes out of the 126 MB L2
+// 256-bit accesses (one 32-byte sector-pair per thread) halve the number of load/store instructions.
+struct V8 {
+    uint32_t r[8];
+};
+__device__ __forceinline__ V8 ldg256_keep(const void* p) {
+    V8 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ V8 ldg256_stream(const void* p) {
+    V8 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg256_stream(void* p, const V8& v) {
+    asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(v.r[0]), "r"(v.r[1]),
+                 "r"(v.r[2]), "r"(v.r[3]), "r"(v.r[4]), "r"(v.r[5]), "r"(v.r[6]), "r"(v.r[7]), "l"(p)
+                 : "memory");
+}
+// 128-bit / 64-bit forms (tile rows and cell rows of CLAHE) take an explicit policy word.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int4 ldg128_hint(const void* p, uint64_t pol) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg64_hint(const void* p, uint64_t pol) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void stg64_hint(void* p, uint2 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
 
 // Byte k of a packed word, zero extended (one PRMT).
 template <int K>
@@ -60,50 +107,42 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t w) { return __byte_perm(w, 
 // A span is n contiguous bytes.  `tid`/`nthr` select the participating threads (a whole CTA for flat planes, one
 // warp for one row of a strided plane).  Unaligned heads/tails are handled with byte accesses.
 struct SpanSplit {
-    uint32_t head;  // bytes before the first 16-byte aligned address
-    uint32_t nvec;  // number of 16-byte vectors (a span is one chunk or one row: far below 2^32 vectors)
+    uint32_t head;  // bytes before the first 32-byte aligned address
+    uint32_t nvec;  // number of 32-byte vectors (a span is one chunk or one row: far below 2^32 vectors)
     size_t tail0;   // offset of the first tail byte
 };
 __device__ __forceinline__ SpanSplit split_span(const void* p, size_t n) {
     SpanSplit s;
-    const size_t mis = (size_t)((16 - ((uintptr_t)p & 15)) & 15);
+    const size_t mis = (size_t)((32 - ((uintptr_t)p & 31)) & 31);
     s.head = (uint32_t)(mis < n ? mis : n);
-    s.nvec = (uint32_t)((n - s.head) >> 4);
-    s.tail0 = (size_t)s.head + ((size_t)s.nvec << 4);
+    s.nvec = (uint32_t)((n - s.head) >> 5);
+    s.tail0 = (size_t)s.head + ((size_t)s.nvec << 5);
     return s;
 }
 
-// Software-pipelined walk over nvec 16-byte vectors: the loads of round r+1 are issued before round r is consumed,
-// so every thread always has U vector loads in flight while it works (ncu showed the unpipelined loop stalled on
-// long_scoreboard for a third of its samples).
-template <int U, class Load, class Use>
+// Software-pipelined walk over nvec 32-byte vectors, thread `tid` of `nthr` taking vectors tid, tid+nthr, ...
+// Two register slots per thread: a slot is refilled (load of the vector two steps ahead) as soon as it has been
+// consumed, so a thread always has one or two 32-byte loads in flight while it works: 32-64 KB per SM at 1024
+// threads, which covers HBM latency at the per-SM share of the bandwidth.
+template <class Load, class Use>
 __device__ __forceinline__ void pipelined_vectors(uint32_t nvec, int tid, int nthr, Load load, Use use) {
-    const uint32_t step = (uint32_t)nthr * U;
+    const uint32_t K = nvec > (uint32_t)tid ? (nvec - tid + nthr - 1) / nthr : 0u;  // vectors of this thread
+    const uint32_t step = (uint32_t)nthr;
     uint32_t i = tid;
-    // rounds in which all U vectors of this thread are in range
-    uint32_t rounds = (i + step - nthr < nvec) ? (nvec - (i + step - nthr) + step - 1) / step : 0u;
-    int4 cur[U];
+    V8 a, b;
 #pragma unroll
-    for (int u = 0; u < U; ++u) cur[u] = make_int4(0, 0, 0, 0);
-    if (rounds) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) cur[u] = load(i + (uint32_t)u * nthr);
+    for (int j = 0; j < 8; ++j) a.r[j] = b.r[j] = 0;
+    if (K > 0) a = load(i);
+    if (K > 1) b = load(i + step);
+    uint32_t k = 0;
+    for (; k + 2 <= K; k += 2) {
+        use(i, a);
+        if (k + 2 < K) a = load(i + 2 * step);
+        use(i + step, b);
+        if (k + 3 < K) b = load(i + 3 * step);
+        i += 2 * step;
     }
-    for (; rounds; --rounds) {
-        int4 nxt[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) nxt[u] = make_int4(0, 0, 0, 0);
-        if (rounds > 1) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) nxt[u] = load(i + step + (uint32_t)u * nthr);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) use(i + (uint32_t)u * nthr, cur[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
-        i += step;
-    }
-    for (; i < nvec; i += nthr) use(i, load(i));
+    if (k < K) use(i, a);
 }
 
 // A lane-private table lives at 32-bit shared address `lane_base` (= table base + lane*4); the entry of value v
@@ -121,14 +160,18 @@ __device__ __forceinline__ void hist_vec(int4 v, uint32_t lane_base) {
     hist_word((uint32_t)v.z, lane_base);
     hist_word((uint32_t)v.w, lane_base);
 }
+__device__ __forceinline__ void hist_v8(const V8& v, uint32_t lane_base) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hist_word(v.r[j], lane_base);
+}
 
-template <int U>
 __device__ __forceinline__ void hist_span(const uint8_t* __restrict__ p, size_t n, int tid, int nthr, uint32_t lane_base) {
     const SpanSplit s = split_span(p, n);
     for (uint32_t i = tid; i < s.head; i += nthr) hist_byte(p[i], lane_base);
-    const int4* v = reinterpret_cast<const int4*>(p + s.head);
-    pipelined_vectors<U>(
-        s.nvec, tid, nthr, [&](uint32_t i) { return ld_keep(v + i); }, [&](uint32_t, int4 x) { hist_vec(x, lane_base); });
+    const uint8_t* v = p + s.head;
+    pipelined_vectors(
+        s.nvec, tid, nthr, [&](uint32_t i) { return ldg256_keep(v + (size_t)i * 32); },
+        [&](uint32_t, const V8& x) { hist_v8(x, lane_base); });
     for (size_t j = s.tail0 + tid; j < n; j += nthr) hist_byte(p[j], lane_base);
 }
 
@@ -152,48 +195,54 @@ __device__ __forceinline__ int4 lut_vec(int4 v, uint32_t lane_base) {
 }
 __device__ __forceinline__ uint8_t lut_byte(uint8_t v, uint32_t lane_base) { return (uint8_t)lds_u32(lane_base + ((uint32_t)v << 7)); }
 
-// dst[i] = table[src[i]] over a span.  src and dst must be congruent mod 16 for the vector path; otherwise the
+__device__ __forceinline__ V8 lut_v8(const V8& v, uint32_t lane_base) {
+    V8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.r[j] = lut_word(v.r[j], lane_base);
+    return o;
+}
+
+// dst[i] = table[src[i]] over a span.  src and dst must be congruent mod 32 for the vector path; otherwise the
 // whole span goes through the byte path (correct, slow, only hit by exotic pointer/pitch combinations).
-template <int U>
 __device__ __forceinline__ void lut_span(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n, int tid,
                                          int nthr, uint32_t lane_base) {
-    if ((((uintptr_t)src ^ (uintptr_t)dst) & 15) != 0) {
+    if ((((uintptr_t)src ^ (uintptr_t)dst) & 31) != 0) {
         for (size_t i = tid; i < n; i += nthr) dst[i] = lut_byte(src[i], lane_base);
         return;
     }
     const SpanSplit s = split_span(src, n);
     for (uint32_t i = tid; i < s.head; i += nthr) dst[i] = lut_byte(src[i], lane_base);
-    const int4* v = reinterpret_cast<const int4*>(src + s.head);
-    int4* o = reinterpret_cast<int4*>(dst + s.head);
-    pipelined_vectors<U>(
-        s.nvec, tid, nthr, [&](uint32_t i) { return ld_stream(v + i); },
-        [&](uint32_t i, int4 x) { st_stream(o + i, lut_vec(x, lane_base)); });
+    const uint8_t* v = src + s.head;
+    uint8_t* o = dst + s.head;
+    pipelined_vectors(
+        s.nvec, tid, nthr, [&](uint32_t i) { return ldg256_stream(v + (size_t)i * 32); },
+        [&](uint32_t i, const V8& x) { stg256_stream(o + (size_t)i * 32, lut_v8(x, lane_base)); });
     for (size_t j = s.tail0 + tid; j < n; j += nthr) dst[j] = lut_byte(src[j], lane_base);
 }
 
-template <int U>
 __device__ __forceinline__ void copy_span(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t n, int tid,
                                           int nthr) {
-    if ((((uintptr_t)src ^ (uintptr_t)dst) & 15) != 0) {
+    if ((((uintptr_t)src ^ (uintptr_t)dst) & 31) != 0) {
         for (size_t i = tid; i < n; i += nthr) dst[i] = src[i];
         return;
     }
     const SpanSplit s = split_span(src, n);
     for (uint32_t i = tid; i < s.head; i += nthr) dst[i] = src[i];
-    const int4* v = reinterpret_cast<const int4*>(src + s.head);
-    int4* o = reinterpret_cast<int4*>(dst + s.head);
-    pipelined_vectors<U>(
-        s.nvec, tid, nthr, [&](uint32_t i) { return ld_stream(v + i); }, [&](uint32_t i, int4 x) { st_stream(o + i, x); });
+    const uint8_t* v = src + s.head;
+    uint8_t* o = dst + s.head;
+    pipelined_vectors(
+        s.nvec, tid, nthr, [&](uint32_t i) { return ldg256_stream(v + (size_t)i * 32); },
+        [&](uint32_t i, const V8& x) { stg256_stream(o + (size_t)i * 32, x); });
     for (size_t j = s.tail0 + tid; j < n; j += nthr) dst[j] = src[j];
 }
 
 __device__ __forceinline__ void fill_span(uint8_t* __restrict__ dst, size_t n, int tid, int nthr, uint8_t value) {
     const SpanSplit s = split_span(dst, n);
     for (uint32_t i = tid; i < s.head; i += nthr) dst[i] = value;
-    int4* o = reinterpret_cast<int4*>(dst + s.head);
-    const int w = (int)(value * 0x01010101u);
-    const int4 vv = make_int4(w, w, w, w);
-    for (uint32_t i = tid; i < s.nvec; i += nthr) st_stream(o + i, vv);
+    V8 vv;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) vv.r[j] = value * 0x01010101u;
+    for (uint32_t i = tid; i < s.nvec; i += nthr) stg256_stream(dst + s.head + (size_t)i * 32, vv);
     for (size_t j = s.tail0 + tid; j < n; j += nthr) dst[j] = value;
 }
 

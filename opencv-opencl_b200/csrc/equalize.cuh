@@ -131,13 +131,13 @@ __device__ __forceinline__ void equalize_uv_chunk(const EqParams& p, const uint8
     const PlaneChunk uc = plane_chunk(p.flat, c, p.uv_bytes, p.uv_chunk, p.h / 2, p.uv_rows_chunk);
     if (p.flat) {
         const size_t n = (size_t)(uc.b1 - uc.b0);
-        if (copy_uv) copy_span<2>(src + uv_off + uc.b0, dst + uv_off + uc.b0, n, tid, nthr);
+        if (copy_uv) copy_span(src + uv_off + uc.b0, dst + uv_off + uc.b0, n, tid, nthr);
         else fill_span(dst + uv_off + uc.b0, n, tid, nthr, 128);
     } else {
         const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
         for (int r = uc.r0 + w; r < uc.r1; r += nw) {
             const size_t off = uv_off + (size_t)r * p.stride;
-            if (copy_uv) copy_span<2>(src + off, dst + off, (size_t)p.w, lane, 32);
+            if (copy_uv) copy_span(src + off, dst + off, (size_t)p.w, lane, 32);
             else fill_span(dst + off, (size_t)p.w, lane, 32, 128);
         }
     }
@@ -180,10 +180,10 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
             __syncthreads();
             const PlaneChunk pc = plane_chunk(p.flat, c, p.y_bytes, p.y_chunk, p.h, p.y_rows_chunk);
             if (p.flat) {
-                hist_span<2>(y + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, lane_base);
+                hist_span(y + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, lane_base);
             } else {
                 for (int r = pc.r0 + warp; r < pc.r1; r += kWarps)
-                    hist_span<2>(y + (size_t)r * p.stride, (size_t)p.w, lane, 32, lane_base);
+                    hist_span(y + (size_t)r * p.stride, (size_t)p.w, lane, 32, lane_base);
             }
             __syncthreads();
             if (tid < 256) {
@@ -232,10 +232,10 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
             __syncthreads();
             const PlaneChunk pc = plane_chunk(p.flat, c, p.y_bytes, p.y_chunk, p.h, p.y_rows_chunk);
             if (p.flat) {
-                lut_span<2>(src + pc.b0, dst + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, lane_base);
+                lut_span(src + pc.b0, dst + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, lane_base);
             } else {
                 for (int r = pc.r0 + warp; r < pc.r1; r += kWarps)
-                    lut_span<2>(src + (size_t)r * p.stride, dst + (size_t)r * p.stride, (size_t)p.w, lane, 32, lane_base);
+                    lut_span(src + (size_t)r * p.stride, dst + (size_t)r * p.stride, (size_t)p.w, lane, 32, lane_base);
             }
         }
         q.advance();

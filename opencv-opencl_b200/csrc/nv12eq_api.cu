@@ -242,7 +242,8 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
     // The Y planes of `lag` frames have to stay in L2 for the second read: cap the footprint at ~64 MB.
     {
         const long long grid_ctas = (long long)ctx->sm_count * per_sm;
-        long long lag = (grid_ctas + 2 * C - 1) / (2 * C) + 1;
+        // measured on B200 (tools/sweep.py): the best lag is ceil(grid / items_per_slot + 0.6)
+        long long lag = (10 * grid_ctas + 6 * 2 * C + 10 * 2 * C - 1) / (10 * 2 * C);
         const long long cap = std::max<long long>(1, (48ll << 20) / (long long)std::max<unsigned long long>(1, p.y_bytes));
         lag = std::min(lag, cap);
         if (ctx->tune_lag > 0) lag = ctx->tune_lag;
