@@ -12,8 +12,9 @@
 //              in the tile reader; the padded image is never materialised.
 //   cell item  (frame f = g - lag, interpolation cell (i, j)): a cell is a rectangle of pixels that blend the same
 //              four tile LUTs.  The CTA packs those four LUTs into table[v][16] = {bf16 L11,L12,L21,L22} (exact:
-//              0..255 fit bf16; widening bf16->fp32 is a shift), then every pixel does ONE 8-byte conflict-free
-//              shared gather and OpenCV's blend op for op in unfused fp32:
+//              0..255 fit bf16 and widening bf16->fp32 is a shift; 16 replicas make a half-warp 8-byte gather
+//              conflict-free), then every pixel does ONE shared gather and OpenCV's blend op for op in unfused fp32
+//              (products two pixels at a time with FMUL2, sums as scalar FADD so that nothing is contracted):
 //                  res = (L11*xa1 + L12*xa)*ya1 + (L21*xa1 + L22*xa)*ya ;  dst = saturate(cvRound(res))
 //   uv item    (frame f, chunk): chroma passthrough / 128 fill.
 //
@@ -25,6 +26,10 @@
 namespace nv12eq {
 
 constexpr int kMaxCells = 4096;  // per axis (tiles + 1); plenty
+#ifndef NV12EQ_PREFETCH_ROUNDS
+#define NV12EQ_PREFETCH_ROUNDS 10
+#endif
+constexpr int kPrefetchRounds = NV12EQ_PREFETCH_ROUNDS;  // L2 prefetch distance of the row-strided walkers
 
 struct ClaheParams {
     const uint8_t* in;
@@ -49,9 +54,9 @@ struct ClaheParams {
     int lag;
     uint8_t* luts;         // [n_frames][tx*ty][256]
     uint32_t* tiles_done;  // [n_frames] self-cleaned
-    uint32_t* applied;     // [n_frames] self-cleaned
     uint32_t* ticket;      // [1] self-cleaned
     uint32_t* status;      // [1]
+    unsigned long long* trace;  // optional [items][4] (developer tool)
 };
 
 __device__ __forceinline__ int reflect101(int p, int len) {
@@ -99,19 +104,40 @@ __device__ __forceinline__ void clahe_tile_lut_warp(const uint32_t* __restrict__
     reinterpret_cast<uint2*>(glut)[lane] = make_uint2(lo, hi);
 }
 
-// bf16x2 word -> two exact floats
+// bf16 halves of a word -> exact floats
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-// One pixel of the blend; e = {L11|L12<<16, L21|L22<<16} as bf16 pairs.  Returns the float whose LOW BYTE is the
-// result: res is a convex-ish combination of values in [0,255], so 0 <= res < 255.5 (the weights sum to 1 within a
-// few ulp); adding 1.5*2^23 performs cvRound's round-half-to-even in the FADD and leaves the integer 0..255 in the
-// low mantissa byte -- saturate_cast is the identity here, so no clamp instructions are needed.
+// One pixel of the blend (general path); e = {L11|L12<<16, L21|L22<<16} as bf16 pairs.  Returns the float whose LOW
+// BYTE is the result: res is a convex-ish combination of values in [0,255], so 0 <= res < 255.5 (the weights sum to 1
+// within a few ulp); adding 1.5*2^23 performs cvRound's round-half-to-even in the FADD and leaves the integer 0..255
+// in the low mantissa byte -- saturate_cast is the identity here, so no clamp instructions are needed.
 __device__ __forceinline__ uint32_t clahe_blend_bits(uint2 e, float xa, float xa1, float ya, float ya1) {
     const float top = __fadd_rn(__fmul_rn(bf16_lo(e.x), xa1), __fmul_rn(bf16_hi(e.x), xa));
     const float bot = __fadd_rn(__fmul_rn(bf16_lo(e.y), xa1), __fmul_rn(bf16_hi(e.y), xa));
     const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
     return __float_as_uint(__fadd_rn(res, 12582912.0f));
+}
+// Two horizontally adjacent pixels at once: the six products per pixel are issued as FMUL2 (two pixels per
+// instruction), the three sums per pixel as scalar FADD, the rounding add as FADD2.  Same operations, same order,
+// same rounding as the scalar form above.
+__device__ __forceinline__ void clahe_blend_pair(uint2 e0, uint2 e1, uint64_t xa_p, uint64_t xa1_p, uint64_t ya_p, uint64_t ya1_p,
+                                                 uint32_t& o0, uint32_t& o1) {
+    const uint64_t a = pack_f2(bf16_lo(e0.x), bf16_lo(e1.x));  // L11 of both pixels
+    const uint64_t b = pack_f2(bf16_hi(e0.x), bf16_hi(e1.x));  // L12
+    const uint64_t c = pack_f2(bf16_lo(e0.y), bf16_lo(e1.y));  // L21
+    const uint64_t d = pack_f2(bf16_hi(e0.y), bf16_hi(e1.y));  // L22
+    float p0, p1, q0, q1;
+    unpack_f2(mul_f2(a, xa1_p), p0, p1);
+    unpack_f2(mul_f2(b, xa_p), q0, q1);
+    const uint64_t top = pack_f2(__fadd_rn(p0, q0), __fadd_rn(p1, q1));
+    unpack_f2(mul_f2(c, xa1_p), p0, p1);
+    unpack_f2(mul_f2(d, xa_p), q0, q1);
+    const uint64_t bot = pack_f2(__fadd_rn(p0, q0), __fadd_rn(p1, q1));
+    unpack_f2(mul_f2(top, ya1_p), p0, p1);
+    unpack_f2(mul_f2(bot, ya_p), q0, q1);
+    const uint64_t res = add_f2(pack_f2(__fadd_rn(p0, q0), __fadd_rn(p1, q1)), pack_f2(12582912.0f, 12582912.0f));
+    unpack_u2(res, o0, o1);
 }
 // low bytes of four words -> one packed word (3 PRMT)
 __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -125,7 +151,9 @@ __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float&
     a1 = __fsub_rn(1.0f, a);
 }
 // keeps a value in its register: stops the compiler from re-deriving xa1 = 1 - xa inside the pixel loop
+__device__ __forceinline__ void pin_register(uint64_t& v) { asm volatile("" : "+l"(v)); }
 __device__ __forceinline__ void pin_register(float& v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ void pin_register(uint32_t& v) { asm volatile("" : "+r"(v)); }
 
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClaheParams p) {
@@ -146,14 +174,15 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
     q.start();
     for (;;) {
         const uint32_t item = q.current();
-        if (item >= total_items) {
-            q.finish(item, total_items);
-            break;
-        }
+        if (item >= total_items) break;
         q.prefetch();
         const int g = (int)(item / (uint32_t)per_slot);
         const int r = (int)(item % (uint32_t)per_slot);
         const int f = g - p.lag;
+        const ItemTrace tr_{p.trace};
+        tr_.mark(item, 0);
+        tr_.mark(item, 1);
+        tr_.kind(item, r < T ? 1u : (r < T + I ? 2u : 3u));
 
         if (r < T) {
             if (g < p.n_frames) {
@@ -240,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 }
                 __syncthreads();
                 if (!s_flag) break;
+                tr_.mark(item, 1);
                 const int ci = r - T;
                 const int cy = ci / p.nxc, cx = ci - cy * p.nxc;
                 const int4 xc = p.xcells[cx], yc = p.ycells[cy];
@@ -260,7 +290,8 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                     for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & 15] = e;
                 }
                 __syncthreads();
-                const uint32_t rep_base = smem_base + (uint32_t)(lane & 15) * 8u;
+                uint32_t rep_base = smem_base + (uint32_t)(lane & 15) * 8u;
+                pin_register(rep_base);
                 const int cw = xc.y - xc.x;                 // cell width in pixels
                 const int gpr = (cw + 7) >> 3;              // 8-pixel groups per row
                 const bool fast = ((xc.x & 7) == 0) && ((p.stride & 7) == 0) && ((((uintptr_t)src | (uintptr_t)dst) & 7) == 0) &&
@@ -271,33 +302,44 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                     const int xg = xc.x + tc * 8;
                     if (tr < rpp) {
                         const int npx = min(8, xc.y - xg);  // < 8 only in the last group of a ragged cell
-                        float xa[8], xa1[8];
+                        uint64_t xa_p[4], xa1_p[4];  // x weights of the pixel pairs (0,1) (2,3) (4,5) (6,7)
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            axis_weight(xg + k, p.inv_tw, xa[k], xa1[k]);
-                            pin_register(xa1[k]);
+                        for (int k = 0; k < 4; ++k) {
+                            float a0, b0, a1, b1;
+                            axis_weight(xg + 2 * k, p.inv_tw, a0, b0);
+                            axis_weight(xg + 2 * k + 1, p.inv_tw, a1, b1);
+                            pin_register(b0);  // xa1 = 1 - xa must stay in a register, not be re-derived per row
+                            pin_register(b1);
+                            xa_p[k] = pack_f2(a0, a1);
+                            xa1_p[k] = pack_f2(b0, b1);
+                            pin_register(xa1_p[k]);
                         }
                         const uint64_t once = l2_policy_evict_first();
                         int yrow = yc.x + tr;
                         const size_t rstep = (size_t)rpp * p.stride;
                         const uint8_t* sp = src + (size_t)yrow * p.stride + xg;
                         uint8_t* dp = dst + (size_t)yrow * p.stride + xg;
-                        uint2 cur = make_uint2(0, 0);
+                        // three rows in flight per thread
+                        uint2 cur = make_uint2(0, 0), n1 = make_uint2(0, 0), n2 = make_uint2(0, 0);
                         if (yrow < yc.y) cur = ldg64_hint(sp, once);
-                        for (; yrow < yc.y; yrow += rpp, sp += rstep, dp += rstep) {
-                            uint2 nxt = make_uint2(0, 0);
-                            if (yrow + rpp < yc.y) nxt = ldg64_hint(sp + rstep, once);
+                        if (yrow + rpp < yc.y) n1 = ldg64_hint(sp + rstep, once);
+                        if (yrow + 2 * rpp < yc.y) n2 = ldg64_hint(sp + 2 * rstep, once);
+                        const uint8_t* sp3 = sp + 3 * rstep;
+                        for (; yrow < yc.y; yrow += rpp, sp3 += rstep, dp += rstep) {
+                            uint2 n3 = make_uint2(0, 0);
+                            if (yrow + 3 * rpp < yc.y) n3 = ldg64_hint(sp3, once);
                             float ya, ya1;
                             axis_weight(yrow, p.inv_th, ya, ya1);
+                            const uint64_t ya_p = pack_f2(ya, ya), ya1_p = pack_f2(ya1, ya1);
                             uint32_t o[8];
-                            o[0] = clahe_blend_bits(lds_u64(rep_base + (byte_of<0>(cur.x) << 7)), xa[0], xa1[0], ya, ya1);
-                            o[1] = clahe_blend_bits(lds_u64(rep_base + (byte_of<1>(cur.x) << 7)), xa[1], xa1[1], ya, ya1);
-                            o[2] = clahe_blend_bits(lds_u64(rep_base + (byte_of<2>(cur.x) << 7)), xa[2], xa1[2], ya, ya1);
-                            o[3] = clahe_blend_bits(lds_u64(rep_base + (byte_of<3>(cur.x) << 7)), xa[3], xa1[3], ya, ya1);
-                            o[4] = clahe_blend_bits(lds_u64(rep_base + (byte_of<0>(cur.y) << 7)), xa[4], xa1[4], ya, ya1);
-                            o[5] = clahe_blend_bits(lds_u64(rep_base + (byte_of<1>(cur.y) << 7)), xa[5], xa1[5], ya, ya1);
-                            o[6] = clahe_blend_bits(lds_u64(rep_base + (byte_of<2>(cur.y) << 7)), xa[6], xa1[6], ya, ya1);
-                            o[7] = clahe_blend_bits(lds_u64(rep_base + (byte_of<3>(cur.y) << 7)), xa[7], xa1[7], ya, ya1);
+                            clahe_blend_pair(lds_u64(rep_base + (byte_of<0>(cur.x) << 7)), lds_u64(rep_base + (byte_of<1>(cur.x) << 7)),
+                                             xa_p[0], xa1_p[0], ya_p, ya1_p, o[0], o[1]);
+                            clahe_blend_pair(lds_u64(rep_base + (byte_of<2>(cur.x) << 7)), lds_u64(rep_base + (byte_of<3>(cur.x) << 7)),
+                                             xa_p[1], xa1_p[1], ya_p, ya1_p, o[2], o[3]);
+                            clahe_blend_pair(lds_u64(rep_base + (byte_of<0>(cur.y) << 7)), lds_u64(rep_base + (byte_of<1>(cur.y) << 7)),
+                                             xa_p[2], xa1_p[2], ya_p, ya1_p, o[4], o[5]);
+                            clahe_blend_pair(lds_u64(rep_base + (byte_of<2>(cur.y) << 7)), lds_u64(rep_base + (byte_of<3>(cur.y) << 7)),
+                                             xa_p[3], xa1_p[3], ya_p, ya1_p, o[6], o[7]);
                             if (npx == 8) {
                                 stg64_hint(dp, make_uint2(pack_low_bytes(o[0], o[1], o[2], o[3]), pack_low_bytes(o[4], o[5], o[6], o[7])),
                                            once);
@@ -306,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                                 for (int k = 0; k < 8; ++k)
                                     if (k < npx) dp[k] = (uint8_t)o[k];
                             }
-                            cur = nxt;
+                            cur = n1; n1 = n2; n2 = n3;
                         }
                     }
                 } else {
@@ -343,15 +385,13 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                     }
                 }
             }
-            // Every apply-side item of frame f has passed its tiles_done wait once it gets here; the last one to
-            // check in returns the counters to zero for the next launch (the LUT storage needs no cleaning).
-            if (tid == 0 && atomicAdd(p.applied + f, 1u) == (uint32_t)(I + U - 1)) {
-                p.tiles_done[f] = 0;
-                p.applied[f] = 0;
-            }
         }
+        tr_.mark(item, 2);
         q.advance();
     }
+    // the last CTA out returns the per-frame counters to zero for the next launch
+    if (q.finish())
+        for (int i = tid; i < p.n_frames; i += kThreads) p.tiles_done[i] = 0;
 }
 
 }  // namespace nv12eq

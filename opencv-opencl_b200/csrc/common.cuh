@@ -36,6 +36,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
@@ -72,6 +77,8 @@ __device__ __forceinline__ void stg256_stream(void* p, const V8& v) {
                  "r"(v.r[2]), "r"(v.r[3]), "r"(v.r[4]), "r"(v.r[5]), "r"(v.r[6]), "r"(v.r[7]), "l"(p)
                  : "memory");
 }
+// Pull a line into L2 ahead of its use without tying up a register (row-strided walkers issue this many rows ahead).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 128-bit / 64-bit forms (tile rows and cell rows of CLAHE) take an explicit policy word.
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
@@ -277,6 +284,28 @@ __device__ __forceinline__ void lane_table_fill_from_lut(uint32_t* tab, const ui
     for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & 7] = q;
 }
 
+// ---- packed fp32 (sm_100 FMUL2 / FADD2): two IEEE round-to-nearest operations per issue slot ------------------
+// NOTE: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even though both carry .rn, which would break bit-exactness
+// with OpenCV's unfused arithmetic.  So products are packed (FMUL2) but the sums that consume them stay scalar
+// add.rn.f32 (never fused); only the final magic-number add, whose inputs are sums, is packed again (FADD2).
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void unpack_u2(uint64_t v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul_f2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ---- warp scan ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -303,12 +332,34 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t k) {
 // construction: an item only waits on items with smaller tickets, and those are resident or finished.
 constexpr long long kSpinCycles = 4ll << 30;
 
+// Optional per-item trace (developer tool, tools/trace_items.py): {start ns, dependency-ready ns, end ns, kind | smid<<8}.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t sm_id() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+struct ItemTrace {
+    unsigned long long* buf;  // [items][4] or null
+    __device__ __forceinline__ void mark(uint32_t item, int slot) const {
+        if (buf && threadIdx.x == 0) buf[(size_t)item * 4 + slot] = global_ns();
+    }
+    __device__ __forceinline__ void kind(uint32_t item, uint32_t k) const {
+        if (buf && threadIdx.x == 0) buf[(size_t)item * 4 + 3] = (unsigned long long)k | ((unsigned long long)sm_id() << 8);
+    }
+};
+
 // Work tickets.  Thread 0 draws the NEXT ticket at the start of an item and publishes it at the end, so the
-// global-atomic round trip is hidden behind the item's work.  Every CTA draws exactly one ticket >= total; the
-// CTA that draws the last of those resets the counter for the next launch.
+// global-atomic round trip is hidden behind the item's work.  Every CTA draws exactly one ticket >= total and then
+// checks out on an exit counter; the last CTA to check out (all work in the grid is finished by then) returns the
+// counters to zero for the next launch -- see the `last_out` result of finish().
 struct TicketQueue {
-    uint32_t* counter;
-    uint32_t* slots;  // shared uint32[2]
+    uint32_t* counter;   // [0] ticket, [2] exit count  (misc workspace words)
+    uint32_t* slots;     // shared uint32[2]
     uint32_t pending;
     uint32_t round;
     __device__ __forceinline__ void start() {
@@ -326,8 +377,21 @@ struct TicketQueue {
         ++round;
         __syncthreads();
     }
-    __device__ __forceinline__ void finish(uint32_t item, uint32_t total) {
-        if (threadIdx.x == 0 && item == total + gridDim.x - 1) atomicExch(counter, 0u);
+    // Call once, by all threads, when the CTA has no more work.  Returns true (to every thread) in the last CTA.
+    __device__ __forceinline__ bool finish() {
+        __shared__ int s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const bool last = atomicAdd(counter + 2, 1u) == gridDim.x - 1;
+            if (last) {
+                counter[0] = 0;
+                counter[2] = 0;
+            }
+            s_last = last;
+        }
+        __syncthreads();
+        return s_last != 0;
     }
 };
 

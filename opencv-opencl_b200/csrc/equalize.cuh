@@ -162,10 +162,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
     q.start();
     for (;;) {
         const uint32_t item = q.current();
-        if (item >= total_items) {
-            q.finish(item, total_items);
-            break;
-        }
+        if (item >= total_items) break;
         q.prefetch();
         const int g = (int)(item / (uint32_t)(2 * C));
         const int r2 = (int)(item % (uint32_t)(2 * C));
@@ -240,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
         }
         q.advance();
     }
+    q.finish();
 }
 
 // ---- Appendix B synthetic frames, generated on the device (bench / test utility) -------------------------

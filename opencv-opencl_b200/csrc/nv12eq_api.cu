@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -381,7 +382,6 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     p.uv_chunks = U;
     p.luts = reinterpret_cast<uint8_t*>(ws.luts.p);
     p.tiles_done = ws_counter(ws, 0);
-    p.applied = ws_counter(ws, 1);
     p.ticket = ws_ticket(ws);
     p.status = ws_status(ws);
 
@@ -399,11 +399,31 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     }
     const long long items = (long long)(n + p.lag) * per_slot;
     if (items >= (1ll << 32)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "too many work items");
+    // developer tool: NV12EQ_TRACE=<file> dumps per-item timestamps of this launch (synchronous, slow)
+    DevBuf trace_buf;
+    const char* trace_path = getenv("NV12EQ_TRACE");
+    if (trace_path) {
+        rc = dev_reserve(ctx, trace_buf, (size_t)items * 4 * sizeof(unsigned long long), true);
+        if (rc) return rc;
+        p.trace = reinterpret_cast<unsigned long long*>(trace_buf.p);
+    }
     const int grid = grid_for(ctx, items, 2);
     if (per_sm <= 1) clahe_kernel<1><<<grid, kThreads, kLaneTableBytes, st>>>(p);
     else clahe_kernel<2><<<grid, kThreads, kLaneTableBytes, st>>>(p);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
+    if (trace_path) {
+        std::vector<unsigned long long> h((size_t)items * 4);
+        CK(ctx, cudaStreamSynchronize(st));
+        CK(ctx, cudaMemcpy(h.data(), trace_buf.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (FILE* fp = fopen(trace_path, "wb")) {
+            const long long hdr[8] = {items, per_slot, T, (long long)p.nxc * p.nyc, U, p.lag, grid, n};
+            fwrite(hdr, sizeof hdr, 1, fp);
+            fwrite(h.data(), sizeof(unsigned long long), h.size(), fp);
+            fclose(fp);
+        }
+        dev_release(trace_buf);
+    }
     return NV12EQ_OK;
 }
 
