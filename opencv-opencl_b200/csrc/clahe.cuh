@@ -11,11 +11,15 @@
 //              (copyMakeBorder BORDER_REFLECT_101 when the grid does not divide the image) is an index reflection
 //              in the tile reader; the padded image is never materialised.
 //   cell item  (frame f = g - lag, interpolation cell (i, j)): a cell is a rectangle of pixels that blend the same
-//              four tile LUTs.  The CTA packs those four LUTs into table[v][16] = {bf16 L11,L12,L21,L22} (exact:
-//              0..255 fit bf16 and widening bf16->fp32 is a shift; 16 replicas make a half-warp 8-byte gather
-//              conflict-free), then every pixel does ONE shared gather and OpenCV's blend op for op in unfused fp32
-//              (products two pixels at a time with FMUL2, sums as scalar FADD so that nothing is contracted):
-//                  res = (L11*xa1 + L12*xa)*ya1 + (L21*xa1 + L22*xa)*ya ;  dst = saturate(cvRound(res))
+//              four tile LUTs.  The CTA packs those four LUTs into table[v][32] = {bf16 L11 | L21, bf16 L12 | L22}
+//              (exact: 0..255 fit bf16 and widening bf16->fp32 is a shift; one 8-byte replica per lane makes the
+//              gather conflict-free), then every pixel does ONE shared gather and OpenCV's blend op for op in
+//              unfused fp32, the top and bottom row of the 2x2 LUT neighbourhood side by side in packed fp32:
+//                  (top, bot) = (L11, L21)*xa1 + (L12, L22)*xa        FMUL2, FMUL2, FADD2
+//                  res        = top*ya1 + bot*ya                      FMUL2, FADD
+//                  dst        = saturate(cvRound(res))                FADD2 with 1.5*2^23 on a pixel pair, PRMT
+//              Entries are 256 bytes apart, so ONE PRMT turns a pixel byte into the shared address of its entry
+//              (byte 1 = pixel value, byte 0 = lane*8); the histogram of tile items uses the same 256-byte rows.
 //   uv item    (frame f, chunk): chroma passthrough / 128 fill.
 //
 // Roofline: HBM, 3*W*H algorithmic bytes per frame (tile LUTs are 16 KB per frame).  Secondary limiters: shared
@@ -23,13 +27,21 @@
 #pragma once
 #include "common.cuh"
 
+// Dynamic shared memory of clahe_kernel, declared at global scope so that its PTX name is unmangled: the kernel takes
+// its address with `mov.u32 r, nv12eq_smem_rows` -- a link-time constant that ptxas folds into the immediate offset of
+// every LDS / ATOMS / LDGSTS ([R + imm]), instead of carrying a base register and an add per access.
+extern __shared__ __align__(256) uint32_t nv12eq_smem_rows[];
+
 namespace nv12eq {
 
 constexpr int kMaxCells = 4096;  // per axis (tiles + 1); plenty
-#ifndef NV12EQ_PREFETCH_ROUNDS
-#define NV12EQ_PREFETCH_ROUNDS 10
-#endif
-constexpr int kPrefetchRounds = NV12EQ_PREFETCH_ROUNDS;  // L2 prefetch distance of the row-strided walkers
+constexpr int kMaxCellRows = 512;               // rows per interpolation cell (host cuts longer runs)
+constexpr int kRowTableBytes = 256 * 256;       // 256 rows of 256 bytes: hist[bin][32 lanes] u32 or table[v][32 lanes] uint2
+constexpr int kRingDepth = 8;                   // pixel rows in flight per thread in the cell loop (power of two)
+constexpr int kTileDepth = 4;                   // 16-byte tile row pieces in flight per thread in the tile loop
+constexpr int kRingBytes = kRingDepth * kThreads * 8;
+static_assert(kTileDepth * kThreads * 16 <= kRingBytes, "tile ring must fit");
+constexpr int kClaheSmemBytes = kRowTableBytes + kRingBytes;  // dynamic shared memory of clahe_kernel
 
 struct ClaheParams {
     const uint8_t* in;
@@ -63,6 +75,56 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     if (len == 1) return 0;
     while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * (len - 1) - p;
     return p;
+}
+
+// ---- 256-byte-row shared tables -----------------------------------------------------------------------------
+// Row v of the table starts at tbase + v*256.  `lane_off` is this lane's byte offset inside a row (< 256, so it
+// lives in byte 0 of the register); byte K of a packed pixel word goes to byte 1: one PRMT = the whole offset.
+template <int K>
+__device__ __forceinline__ uint32_t row_entry(uint32_t w, uint32_t lane_off) { return __byte_perm(w, lane_off, 0x5504u | (K << 4)); }
+
+// histogram rows: hist[bin][lane] u32 in the first 128 bytes of row `bin`
+__device__ __forceinline__ void hist256_byte(uint32_t v, uint32_t tbase, uint32_t lane4) { red_shared_inc(tbase + (v << 8) + lane4); }
+__device__ __forceinline__ void hist256_word(uint32_t w, uint32_t tbase, uint32_t lane4) {
+    red_shared_inc(tbase + row_entry<0>(w, lane4));
+    red_shared_inc(tbase + row_entry<1>(w, lane4));
+    red_shared_inc(tbase + row_entry<2>(w, lane4));
+    red_shared_inc(tbase + row_entry<3>(w, lane4));
+}
+__device__ __forceinline__ void hist256_vec(int4 v, uint32_t tbase, uint32_t lane4) {
+    hist256_word((uint32_t)v.x, tbase, lane4);
+    hist256_word((uint32_t)v.y, tbase, lane4);
+    hist256_word((uint32_t)v.z, tbase, lane4);
+    hist256_word((uint32_t)v.w, tbase, lane4);
+}
+// n contiguous bytes by one warp (general tile path): 16-byte vectors where alignment allows, bytes elsewhere
+__device__ __forceinline__ void hist256_span_warp(const uint8_t* __restrict__ p, int n, int lane, uint32_t tbase, uint32_t lane4,
+                                                  uint64_t pol) {
+    const int mis = (int)((16 - ((uintptr_t)p & 15)) & 15);
+    const int head = min(mis, n);
+    for (int i = lane; i < head; i += 32) hist256_byte(p[i], tbase, lane4);
+    const int nvec = (n - head) >> 4;
+    const uint8_t* v = p + head;
+    for (int i = lane; i < nvec; i += 32) hist256_vec(ldg128_hint(v + (size_t)i * 16, pol), tbase, lane4);
+    for (int i = head + (nvec << 4) + lane; i < n; i += 32) hist256_byte(p[i], tbase, lane4);
+}
+__device__ __forceinline__ void hist256_zero(uint32_t* tab) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 2048 / kThreads; ++k) {
+        const int i = threadIdx.x + k * kThreads;  // 16-byte slot i of the used halves: row i>>3, column i&7
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(tab) + (i >> 3) * 256 + (i & 7) * 16) = z;
+    }
+}
+__device__ __forceinline__ uint32_t hist256_row_sum(const uint32_t* tab, int bin) {
+    const uint8_t* row = reinterpret_cast<const uint8_t*>(tab) + bin * 256;
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint4 q = *reinterpret_cast<const uint4*>(row + ((j + bin) & 7) * 16);
+        s += q.x + q.y + q.z + q.w;
+    }
+    return s;
 }
 
 // One warp: tile histogram (shared, 256 ints) -> clip -> redistribute -> scan -> LUT bytes (global).
@@ -104,44 +166,57 @@ __device__ __forceinline__ void clahe_tile_lut_warp(const uint32_t* __restrict__
     reinterpret_cast<uint2*>(glut)[lane] = make_uint2(lo, hi);
 }
 
-// bf16 halves of a word -> exact floats
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-
-// One pixel of the blend (general path); e = {L11|L12<<16, L21|L22<<16} as bf16 pairs.  Returns the float whose LOW
-// BYTE is the result: res is a convex-ish combination of values in [0,255], so 0 <= res < 255.5 (the weights sum to 1
-// within a few ulp); adding 1.5*2^23 performs cvRound's round-half-to-even in the FADD and leaves the integer 0..255
-// in the low mantissa byte -- saturate_cast is the identity here, so no clamp instructions are needed.
-__device__ __forceinline__ uint32_t clahe_blend_bits(uint2 e, float xa, float xa1, float ya, float ya1) {
-    const float top = __fadd_rn(__fmul_rn(bf16_lo(e.x), xa1), __fmul_rn(bf16_hi(e.x), xa));
-    const float bot = __fadd_rn(__fmul_rn(bf16_lo(e.y), xa1), __fmul_rn(bf16_hi(e.y), xa));
-    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-    return __float_as_uint(__fadd_rn(res, 12582912.0f));
+// ---- the blend ------------------------------------------------------------------------------------------------
+// Table entry e = {bf16 L11 | bf16 L21 << 16, bf16 L12 | bf16 L22 << 16}; yw = (ya1, ya) packed.
+// The sum of the two packed products is an add.rn.FTZ.f32x2: ptxas contracts a plain add.rn.f32x2 of mul.rn.f32x2
+// results into FFMA2 (even with -fmad=false), which rounds once instead of twice and breaks bit-exactness with
+// OpenCV's unfused arithmetic; it does not contract across an .ftz mismatch.  FTZ itself is value-neutral here: the
+// operands are products of integers 0..255 and weights that are 0 or >= 2^-25, never subnormal.
+// (tests/test_abi.py checks that the built library contains no FFMA2 at all.)
+__device__ __forceinline__ uint64_t add_f2_nofuse(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
 }
-// Two horizontally adjacent pixels at once: the six products per pixel are issued as FMUL2 (two pixels per
-// instruction), the three sums per pixel as scalar FADD, the rounding add as FADD2.  Same operations, same order,
-// same rounding as the scalar form above.
-__device__ __forceinline__ void clahe_blend_pair(uint2 e0, uint2 e1, uint64_t xa_p, uint64_t xa1_p, uint64_t ya_p, uint64_t ya1_p,
-                                                 uint32_t& o0, uint32_t& o1) {
-    const uint64_t a = pack_f2(bf16_lo(e0.x), bf16_lo(e1.x));  // L11 of both pixels
-    const uint64_t b = pack_f2(bf16_hi(e0.x), bf16_hi(e1.x));  // L12
-    const uint64_t c = pack_f2(bf16_lo(e0.y), bf16_lo(e1.y));  // L21
-    const uint64_t d = pack_f2(bf16_hi(e0.y), bf16_hi(e1.y));  // L22
-    float p0, p1, q0, q1;
-    unpack_f2(mul_f2(a, xa1_p), p0, p1);
-    unpack_f2(mul_f2(b, xa_p), q0, q1);
-    const uint64_t top = pack_f2(__fadd_rn(p0, q0), __fadd_rn(p1, q1));
-    unpack_f2(mul_f2(c, xa1_p), p0, p1);
-    unpack_f2(mul_f2(d, xa_p), q0, q1);
-    const uint64_t bot = pack_f2(__fadd_rn(p0, q0), __fadd_rn(p1, q1));
-    unpack_f2(mul_f2(top, ya1_p), p0, p1);
-    unpack_f2(mul_f2(bot, ya_p), q0, q1);
-    const uint64_t res = add_f2(pack_f2(__fadd_rn(p0, q0), __fadd_rn(p1, q1)), pack_f2(12582912.0f, 12582912.0f));
-    unpack_u2(res, o0, o1);
+// res of one pixel: 0 <= res < 255.5 (convex-ish combination of values in [0,255]), so adding 1.5*2^23 afterwards
+// performs cvRound's round-half-to-even and leaves the integer in the low mantissa byte; saturate_cast is the identity.
+__device__ __forceinline__ float clahe_blend_res(uint2 e, float xa, float xa1, uint64_t yw) {
+    const uint64_t A = pack_f2(__uint_as_float(e.x << 16), __uint_as_float(e.x & 0xffff0000u));  // (L11, L21)
+    const uint64_t B = pack_f2(__uint_as_float(e.y << 16), __uint_as_float(e.y & 0xffff0000u));  // (L12, L22)
+    const uint64_t S = add_f2_nofuse(mul_f2(A, pack_f2(xa1, xa1)), mul_f2(B, pack_f2(xa, xa)));   // (top, bot)
+    float r0, r1;
+    unpack_f2(mul_f2(S, yw), r0, r1);  // (top*ya1, bot*ya)
+    return __fadd_rn(r0, r1);
+}
+template <int K>
+__device__ __forceinline__ float clahe_blend_px(uint32_t w, uint32_t tbase, uint32_t lane8, float xa, float xa1, uint64_t yw) {
+    return clahe_blend_res(lds_u64(tbase + row_entry<K>(w, lane8)), xa, xa1, yw);
+}
+__device__ __forceinline__ void round_pair(float a, float b, uint32_t& oa, uint32_t& ob) {
+    unpack_u2(add_f2(pack_f2(a, b), pack_f2(12582912.0f, 12582912.0f)), oa, ob);
 }
 // low bytes of four words -> one packed word (3 PRMT)
 __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+// eight horizontally adjacent pixels (two packed words) -> two packed output words
+__device__ __forceinline__ uint2 clahe_blend_8(uint2 px, uint32_t lane8, const float (&xa)[8], const float (&xa1)[8], uint64_t yw) {
+    // re-read the table base here: a fresh uniform value lets ptxas address the gathers as [R + UR] instead of adding
+    // a base held in a vector register to every offset
+    const uint32_t tbase = smem_u32(nv12eq_smem_rows);
+    float f[8];
+    f[0] = clahe_blend_px<0>(px.x, tbase, lane8, xa[0], xa1[0], yw);
+    f[1] = clahe_blend_px<1>(px.x, tbase, lane8, xa[1], xa1[1], yw);
+    f[2] = clahe_blend_px<2>(px.x, tbase, lane8, xa[2], xa1[2], yw);
+    f[3] = clahe_blend_px<3>(px.x, tbase, lane8, xa[3], xa1[3], yw);
+    f[4] = clahe_blend_px<0>(px.y, tbase, lane8, xa[4], xa1[4], yw);
+    f[5] = clahe_blend_px<1>(px.y, tbase, lane8, xa[5], xa1[5], yw);
+    f[6] = clahe_blend_px<2>(px.y, tbase, lane8, xa[6], xa1[6], yw);
+    f[7] = clahe_blend_px<3>(px.y, tbase, lane8, xa[7], xa1[7], yw);
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) round_pair(f[k], f[k + 1], o[k], o[k + 1]);
+    return make_uint2(pack_low_bytes(o[0], o[1], o[2], o[3]), pack_low_bytes(o[4], o[5], o[6], o[7]));
 }
 
 __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float& a1) {
@@ -151,14 +226,13 @@ __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float&
     a1 = __fsub_rn(1.0f, a);
 }
 // keeps a value in its register: stops the compiler from re-deriving xa1 = 1 - xa inside the pixel loop
-__device__ __forceinline__ void pin_register(uint64_t& v) { asm volatile("" : "+l"(v)); }
 __device__ __forceinline__ void pin_register(float& v) { asm volatile("" : "+f"(v)); }
-__device__ __forceinline__ void pin_register(uint32_t& v) { asm volatile("" : "+r"(v)); }
 
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClaheParams p) {
-    extern __shared__ __align__(16) uint32_t smem[];  // 32 KB: hist[256][32] for tile items, table[256][16] uint2 for cells
+    uint32_t* const smem_rows = nv12eq_smem_rows;  // 64 KB of 256-byte rows: hist[bin][32] (tile items) / table[v][32] (cells); then the ring
     __shared__ uint32_t s_bins[256];
+    __shared__ __align__(8) float2 s_yw[kMaxCellRows];  // (ya1, ya) of the rows of the current cell
     __shared__ uint32_t s_ticket[2];
     __shared__ int s_flag;
 
@@ -168,14 +242,16 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
     const int U = p.uv_chunks;
     const int per_slot = T + I + U;
     const uint32_t total_items = (uint32_t)(p.n_frames + p.lag) * (uint32_t)per_slot;
-    const uint32_t smem_base = smem_u32(smem);
+    uint32_t tbase;
+    asm("mov.u32 %0, nv12eq_smem_rows;" : "=r"(tbase));
+    const uint32_t rbase = tbase + kRowTableBytes;  // cp.async ring of the cell loop
+    const uint32_t lane4 = (uint32_t)lane * 4u, lane8 = (uint32_t)lane * 8u;
 
-    TicketQueue q{p.ticket, s_ticket, 0u, 0u};
+    TicketQueue q{p.ticket, s_ticket, 0u, 0u, false};
     q.start();
     for (;;) {
         const uint32_t item = q.current();
         if (item >= total_items) break;
-        q.prefetch();
         const int g = (int)(item / (uint32_t)per_slot);
         const int r = (int)(item % (uint32_t)per_slot);
         const int f = g - p.lag;
@@ -190,56 +266,54 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 const uint8_t* y = p.in + (unsigned long long)g * p.pitch;
                 const int tyi = r / p.tx, txi = r - tyi * p.tx;
                 const int x0 = txi * p.tw, y0 = tyi * p.th;
-                const uint32_t lane_base = smem_base + lane * 4;
-                lane_table_zero(smem);
+                hist256_zero(smem_rows);
                 __syncthreads();
+                const uint64_t keep = l2_policy_evict_last();
                 const bool vec_ok = !p.padded && (p.tw & 15) == 0 && (p.stride & 15) == 0 &&
                                     (((uintptr_t)y + (uintptr_t)x0) & 15) == 0 && (p.tw >> 4) <= kThreads;
                 if (vec_ok) {
-                    // threads form a (rows_per_pass x vectors_per_row) grid over the tile; loads are software pipelined
+                    // threads form a (rows_per_pass x vectors_per_row) grid over the tile.  Every thread keeps
+                    // kTileDepth-1 of its 16-byte row pieces in flight through a private cp.async ring (64 KB per SM).
                     const int vpr = p.tw >> 4;
                     const int rpp = kThreads / vpr;
                     const int tr = tid / vpr, tc = tid - tr * vpr;
-                    if (tr < rpp) {
-                        const uint64_t keep = l2_policy_evict_last();
-                        const uint8_t* col = y + (size_t)y0 * p.stride + x0 + tc * 16;
+                    if (tr < rpp && tr < p.th) {
+                        const uint8_t* ptr = y + (size_t)(y0 + tr) * p.stride + x0 + tc * 16;
                         const size_t rstep = (size_t)rpp * p.stride;
-                        int row = tr;
-                        const uint8_t* ptr = col + (size_t)row * p.stride;
-                        bool have = row + rpp < p.th;  // a full round of 2 rows
-                        int4 c0, c1;
-                        if (have) {
-                            c0 = ldg128_hint(ptr, keep);
-                            c1 = ldg128_hint(ptr + rstep, keep);
+                        const int nrows = (p.th - tr + rpp - 1) / rpp;
+                        const uint32_t ring0 = rbase + (uint32_t)tid * 16u;
+                        constexpr uint32_t kSlot = kThreads * 16u, kRingMask = kTileDepth * kSlot - 1u;
+#pragma unroll
+                        for (int j = 0; j < kTileDepth - 1; ++j) {
+                            if (j < nrows) cp_async16_hint(ring0 + (uint32_t)j * kSlot, ptr + (size_t)j * rstep, keep);
+                            cp_async_commit();
                         }
-                        while (have) {
-                            const int rn = row + 2 * rpp;
-                            const uint8_t* pn = ptr + 2 * rstep;
-                            const bool more = rn + rpp < p.th;
-                            int4 n0, n1;
-                            if (more) {
-                                n0 = ldg128_hint(pn, keep);
-                                n1 = ldg128_hint(pn + rstep, keep);
-                            }
-                            hist_vec(c0, lane_base);
-                            hist_vec(c1, lane_base);
-                            if (more) { c0 = n0; c1 = n1; }
-                            row = rn; ptr = pn; have = more;
+                        const uint8_t* pn = ptr + (size_t)(kTileDepth - 1) * rstep;
+                        uint32_t rd = 0u, wr = (uint32_t)(kTileDepth - 1) * kSlot;
+#pragma unroll 1
+                        for (int i = 0; i < nrows; ++i) {
+                            if (i + kTileDepth - 1 < nrows) cp_async16_hint(ring0 + wr, pn, keep);
+                            cp_async_commit();
+                            cp_async_wait<kTileDepth - 1>();
+                            hist256_vec(lds_s4(ring0 + rd), tbase, lane4);
+                            pn += rstep;
+                            wr = rd;
+                            rd = (rd + kSlot) & kRingMask;
                         }
-                        for (; row < p.th; row += rpp, ptr += rstep) hist_vec(ldg128_hint(ptr, keep), lane_base);
                     }
                 } else {
                     // general path: one warp per tile row, byte spans inside the image, reflected reads outside
                     for (int row = warp; row < p.th; row += kWarps) {
                         const uint8_t* src_row = y + (size_t)reflect101(y0 + row, p.h) * p.stride;
                         const int xin = min(x0 + p.tw, p.w);  // end of the in-image part
-                        if (x0 < xin) hist_span(src_row + x0, (size_t)(xin - x0), lane, 32, lane_base);
+                        if (x0 < xin) hist256_span_warp(src_row + x0, xin - x0, lane, tbase, lane4, keep);
                         for (int x = max(x0, p.w) + lane; x < x0 + p.tw; x += 32)
-                            hist_byte(src_row[reflect101(x, p.w)], lane_base);
+                            hist256_byte(src_row[reflect101(x, p.w)], tbase, lane4);
                     }
                 }
+                q.prefetch();  // the row sums and the LUT build (~1 us) hide the ticket round trip
                 __syncthreads();
-                if (tid < 256) s_bins[tid] = lane_table_row_sum(smem, tid);
+                if (tid < 256) s_bins[tid] = hist256_row_sum(smem_rows, tid);
                 __syncthreads();
                 if (warp == 0) {
                     clahe_tile_lut_warp(s_bins, p.clip_limit, p.lut_scale, p.luts + ((size_t)g * T + r) * 256, lane);
@@ -253,6 +327,16 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
             uint8_t* dst = p.out + (unsigned long long)f * p.pitch;
             if (r < T + I) {
                 // ------------------------- cell item: blend four tile LUTs -------------------------
+                const int ci = r - T;
+                const int cy = ci / p.nxc, cx = ci - cy * p.nxc;
+                const int4 xc = p.xcells[cx], yc = p.ycells[cy];
+                const int cw = xc.y - xc.x, ch = yc.y - yc.x;  // cell size in pixels (ch <= kMaxCellRows)
+                // y weights of the cell's rows (does not depend on the tile LUTs: done before the dependency wait)
+                for (int i = tid; i < ch; i += kThreads) {
+                    float ya, ya1;
+                    axis_weight(yc.x + i, p.inv_th, ya, ya1);
+                    s_yw[i] = make_float2(ya1, ya);
+                }
                 if (tid == 0) {
                     bool ok = true;
                     if (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
@@ -270,12 +354,9 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 __syncthreads();
                 if (!s_flag) break;
                 tr_.mark(item, 1);
-                const int ci = r - T;
-                const int cy = ci / p.nxc, cx = ci - cy * p.nxc;
-                const int4 xc = p.xcells[cx], yc = p.ycells[cy];
-                // pack the four LUTs: table[v][rep] (uint2), 16 replicas so a half-warp 8-byte gather is conflict-free
+                // pack the four LUTs: row v = 32 lane replicas of {bf16 L11 | L21 << 16, bf16 L12 | L22 << 16}
                 {
-                    constexpr int kShare = kThreads / 256, kPer = 16 / kShare;
+                    constexpr int kShare = kThreads / 256, kPer = 32 / kShare;
                     const uint8_t* L = p.luts + (size_t)f * T * 256;
                     const int v = tid & 255, part = tid >> 8;
                     const uint32_t l11 = __ldcg(L + (size_t)(yc.z * p.tx + xc.z) * 256 + v);
@@ -283,90 +364,88 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                     const uint32_t l21 = __ldcg(L + (size_t)(yc.w * p.tx + xc.z) * 256 + v);
                     const uint32_t l22 = __ldcg(L + (size_t)(yc.w * p.tx + xc.w) * 256 + v);
                     uint2 e;
-                    e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l12) & 0xffff0000u);
-                    e.y = (__float_as_uint((float)l21) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
-                    uint2* row = reinterpret_cast<uint2*>(smem) + v * 16;
+                    e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l21) & 0xffff0000u);
+                    e.y = (__float_as_uint((float)l12) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
+                    uint2* row = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(smem_rows) + v * 256);
 #pragma unroll
-                    for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & 15] = e;
+                    for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & 31] = e;
                 }
                 __syncthreads();
-                uint32_t rep_base = smem_base + (uint32_t)(lane & 15) * 8u;
-                pin_register(rep_base);
-                const int cw = xc.y - xc.x;                 // cell width in pixels
-                const int gpr = (cw + 7) >> 3;              // 8-pixel groups per row
+                const uint32_t ywbase = smem_u32(s_yw);
+                // Fast path: full 8-pixel groups, one 8-byte load / store per thread and row.  Columns left over when the cell
+                // width is not a multiple of 8 (and everything when alignment does not allow 8-byte accesses) take the
+                // pixel-at-a-time path below.
                 const bool fast = ((xc.x & 7) == 0) && ((p.stride & 7) == 0) && ((((uintptr_t)src | (uintptr_t)dst) & 7) == 0) &&
-                                  gpr <= kThreads;
+                                  (cw >> 3) >= 1 && (cw >> 3) <= kThreads;
+                const int gpr = fast ? (cw >> 3) : 0;   // 8-pixel groups per row
+                const int xslow = xc.x + gpr * 8;        // first column of the pixel-at-a-time path
                 if (fast) {
                     const int rpp = kThreads / gpr;
                     const int tr = tid / gpr, tc = tid - tr * gpr;
                     const int xg = xc.x + tc * 8;
-                    if (tr < rpp) {
-                        const int npx = min(8, xc.y - xg);  // < 8 only in the last group of a ragged cell
-                        uint64_t xa_p[4], xa1_p[4];  // x weights of the pixel pairs (0,1) (2,3) (4,5) (6,7)
+                    if (tr < rpp && tr < ch) {
+                        float xa[8], xa1[8];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            float a0, b0, a1, b1;
-                            axis_weight(xg + 2 * k, p.inv_tw, a0, b0);
-                            axis_weight(xg + 2 * k + 1, p.inv_tw, a1, b1);
-                            pin_register(b0);  // xa1 = 1 - xa must stay in a register, not be re-derived per row
-                            pin_register(b1);
-                            xa_p[k] = pack_f2(a0, a1);
-                            xa1_p[k] = pack_f2(b0, b1);
-                            pin_register(xa1_p[k]);
-                        }
+                        for (int k = 0; k < 8; ++k) axis_weight(xg + k, p.inv_tw, xa[k], xa1[k]);
                         const uint64_t once = l2_policy_evict_first();
-                        int yrow = yc.x + tr;
                         const size_t rstep = (size_t)rpp * p.stride;
-                        const uint8_t* sp = src + (size_t)yrow * p.stride + xg;
-                        uint8_t* dp = dst + (size_t)yrow * p.stride + xg;
-                        // three rows in flight per thread
-                        uint2 cur = make_uint2(0, 0), n1 = make_uint2(0, 0), n2 = make_uint2(0, 0);
-                        if (yrow < yc.y) cur = ldg64_hint(sp, once);
-                        if (yrow + rpp < yc.y) n1 = ldg64_hint(sp + rstep, once);
-                        if (yrow + 2 * rpp < yc.y) n2 = ldg64_hint(sp + 2 * rstep, once);
-                        const uint8_t* sp3 = sp + 3 * rstep;
-                        for (; yrow < yc.y; yrow += rpp, sp3 += rstep, dp += rstep) {
-                            uint2 n3 = make_uint2(0, 0);
-                            if (yrow + 3 * rpp < yc.y) n3 = ldg64_hint(sp3, once);
-                            float ya, ya1;
-                            axis_weight(yrow, p.inv_th, ya, ya1);
-                            const uint64_t ya_p = pack_f2(ya, ya), ya1_p = pack_f2(ya1, ya1);
-                            uint32_t o[8];
-                            clahe_blend_pair(lds_u64(rep_base + (byte_of<0>(cur.x) << 7)), lds_u64(rep_base + (byte_of<1>(cur.x) << 7)),
-                                             xa_p[0], xa1_p[0], ya_p, ya1_p, o[0], o[1]);
-                            clahe_blend_pair(lds_u64(rep_base + (byte_of<2>(cur.x) << 7)), lds_u64(rep_base + (byte_of<3>(cur.x) << 7)),
-                                             xa_p[1], xa1_p[1], ya_p, ya1_p, o[2], o[3]);
-                            clahe_blend_pair(lds_u64(rep_base + (byte_of<0>(cur.y) << 7)), lds_u64(rep_base + (byte_of<1>(cur.y) << 7)),
-                                             xa_p[2], xa1_p[2], ya_p, ya1_p, o[4], o[5]);
-                            clahe_blend_pair(lds_u64(rep_base + (byte_of<2>(cur.y) << 7)), lds_u64(rep_base + (byte_of<3>(cur.y) << 7)),
-                                             xa_p[3], xa1_p[3], ya_p, ya1_p, o[6], o[7]);
-                            if (npx == 8) {
-                                stg64_hint(dp, make_uint2(pack_low_bytes(o[0], o[1], o[2], o[3]), pack_low_bytes(o[4], o[5], o[6], o[7])),
-                                           once);
-                            } else {
+                        const int nrows = (ch - tr + rpp - 1) / rpp;  // rows of this thread: tr, tr + rpp, ...
+                        const uint8_t* sp = src + (size_t)(yc.x + tr) * p.stride + xg;
+                        uint8_t* dp = dst + (size_t)(yc.x + tr) * p.stride + xg;
+                        uint32_t yw_addr = ywbase + (uint32_t)tr * 8u;
+                        const uint32_t yw_step = (uint32_t)rpp * 8u;
+                        // Thread-private ring of kRingDepth 8-byte slots in shared memory, filled with cp.async: the rows
+                        // kRingDepth-1 ahead are in flight (about 60 KB per SM) without holding registers, and since a
+                        // thread only ever reads its own slots no barrier is involved.
+                        const uint32_t ring0 = rbase + (uint32_t)tid * 8u;
+                        constexpr uint32_t kSlot = kThreads * 8u, kRingMask = kRingDepth * kSlot - 1u;
 #pragma unroll
-                                for (int k = 0; k < 8; ++k)
-                                    if (k < npx) dp[k] = (uint8_t)o[k];
+                        for (int j = 0; j < kRingDepth - 1; ++j) {
+                            if (j < nrows) cp_async8_hint(ring0 + (uint32_t)j * kSlot, sp + (size_t)j * rstep, once);
+                            cp_async_commit();
+                        }
+                        const uint8_t* spn = sp + (size_t)(kRingDepth - 1) * rstep;
+                        uint32_t rd = 0u, wr = (uint32_t)(kRingDepth - 1) * kSlot;
+                        // two passes over one loop body: thread 0 (tr == 0, the most rows) draws the next ticket ~4 rows
+                        // before the end, which hides the atomic's round trip without a test in every iteration
+                        int i = 0;
+#pragma unroll 1
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int iend = pass ? nrows : max(nrows - 4, 0);
+#pragma unroll 1
+                            for (; i < iend; ++i) {
+                                if (i + kRingDepth - 1 < nrows) cp_async8_hint(ring0 + wr, spn, once);
+                                cp_async_commit();
+                                cp_async_wait<kRingDepth - 1>();
+                                const uint2 px = lds_u64(ring0 + rd);
+                                const uint64_t yw = lds_b64(yw_addr);
+                                const uint2 o = clahe_blend_8(px, lane8, xa, xa1, yw);
+                                __stcs(reinterpret_cast<uint2*>(dp), o);
+                                spn += rstep; dp += rstep; yw_addr += yw_step;
+                                wr = rd;
+                                rd = (rd + kSlot) & kRingMask;
                             }
-                            cur = n1; n1 = n2; n2 = n3;
+                            if (pass == 0) q.prefetch();
                         }
                     }
-                } else {
-                    // general path: one pixel per thread per step
-                    const int ch = yc.y - yc.x;
-                    const long long npix = (long long)cw * ch;
+                }
+                if (xslow < xc.y) {
+                    // pixel-at-a-time path
+                    const int sw = xc.y - xslow;
+                    const long long npix = (long long)sw * ch;
                     for (long long i = tid; i < npix; i += kThreads) {
-                        const int ry = (int)(i / cw), rx = (int)(i - (long long)ry * cw);
-                        const int x = xc.x + rx, yy = yc.x + ry;
-                        float xa, xa1, ya, ya1;
+                        const int ry = (int)(i / sw), rx = (int)(i - (long long)ry * sw);
+                        const int x = xslow + rx, yy = yc.x + ry;
+                        float xa, xa1;
                         axis_weight(x, p.inv_tw, xa, xa1);
-                        axis_weight(yy, p.inv_th, ya, ya1);
                         const uint32_t v = src[(size_t)yy * p.stride + x];
-                        dst[(size_t)yy * p.stride + x] = (uint8_t)clahe_blend_bits(lds_u64(rep_base + (v << 7)), xa, xa1, ya, ya1);
+                        const float res = clahe_blend_res(lds_u64(tbase + (v << 8) + lane8), xa, xa1, lds_b64(ywbase + (uint32_t)ry * 8u));
+                        dst[(size_t)yy * p.stride + x] = (uint8_t)__float_as_uint(__fadd_rn(res, 12582912.0f));
                     }
                 }
             } else {
                 // ------------------------- uv item -------------------------
+                q.prefetch();  // short item: draw the next ticket right away
                 const int c = r - T - I;
                 const bool copy_uv = p.uv_mode == UV_COPY && src != dst;
                 const size_t uv_off = (size_t)p.stride * p.h;

@@ -41,9 +41,19 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ int4 lds_s4(uint32_t saddr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ uint2 lds_u64(uint32_t saddr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint64_t lds_b64(uint32_t saddr) {
+    uint64_t v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(saddr));
     return v;
 }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -105,6 +115,19 @@ __device__ __forceinline__ uint2 ldg64_hint(const void* p, uint64_t pol) {
 __device__ __forceinline__ void stg64_hint(void* p, uint2 v, uint64_t pol) {
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
 }
+
+// Asynchronous global -> shared copies (LDGSTS): the data never occupies a register while it is in flight, so a
+// thread can keep many rows outstanding.  Groups are per thread: wait_group<N> returns when all but the newest N
+// committed groups of THIS thread have landed -- a thread that only reads its own slots needs no barrier.
+__device__ __forceinline__ void cp_async8_hint(uint32_t saddr, const void* g, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(saddr), "l"(g), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t saddr, const void* g, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Byte k of a packed word, zero extended (one PRMT).
 template <int K>
@@ -353,27 +376,37 @@ struct ItemTrace {
     }
 };
 
-// Work tickets.  Thread 0 draws the NEXT ticket at the start of an item and publishes it at the end, so the
-// global-atomic round trip is hidden behind the item's work.  Every CTA draws exactly one ticket >= total and then
-// checks out on an exit counter; the last CTA to check out (all work in the grid is finished by then) returns the
-// counters to zero for the next launch -- see the `last_out` result of finish().
+// Work tickets.  Thread 0 draws the NEXT ticket shortly before the end of an item (prefetch(), so that the
+// global-atomic round trip is hidden behind the tail of the item's work) and publishes it at the end.  Drawing it
+// earlier would queue the next item behind the current one while other CTAs may be idle: with items of very
+// different lengths that head-of-line blocking delays the items other CTAs are waiting for.  Every CTA draws exactly
+// one ticket >= total and then checks out on an exit counter; the last CTA to check out (all work in the grid is
+// finished by then) returns the counters to zero for the next launch -- see the `last_out` result of finish().
 struct TicketQueue {
     uint32_t* counter;   // [0] ticket, [2] exit count  (misc workspace words)
     uint32_t* slots;     // shared uint32[2]
     uint32_t pending;
     uint32_t round;
+    bool drawn;          // thread 0: the next ticket has been drawn
     __device__ __forceinline__ void start() {
         round = 0;
+        drawn = false;
         if (threadIdx.x == 0) slots[0] = atomicAdd(counter, 1u);
         __syncthreads();
     }
     __device__ __forceinline__ uint32_t current() const { return slots[round & 1]; }
+    // thread 0 only (other threads: no-op); idempotent within an item
     __device__ __forceinline__ void prefetch() {
-        if (threadIdx.x == 0) pending = atomicAdd(counter, 1u);
+        if (threadIdx.x == 0 && !drawn) {
+            pending = atomicAdd(counter, 1u);
+            drawn = true;
+        }
     }
     // also the end-of-item barrier that protects the shared tables of the next item
     __device__ __forceinline__ void advance() {
+        prefetch();
         if (threadIdx.x == 0) slots[(round + 1) & 1] = pending;
+        drawn = false;
         ++round;
         __syncthreads();
     }

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
     const int lag = (do_hist && do_apply) ? p.lag : 0;
     const uint32_t total_items = (uint32_t)(p.n_frames + lag) * (uint32_t)(2 * C);
 
-    TicketQueue q{p.ticket, s_ticket, 0u, 0u};
+    TicketQueue q{p.ticket, s_ticket, 0u, 0u, false};
     q.start();
     for (;;) {
         const uint32_t item = q.current();

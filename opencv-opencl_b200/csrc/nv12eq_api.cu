@@ -180,8 +180,8 @@ int ensure_attrs(nv12eq_ctx* ctx) {
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
-    CK(ctx, cudaFuncSetAttribute(clahe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
-    CK(ctx, cudaFuncSetAttribute(clahe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(clahe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
+    CK(ctx, cudaFuncSetAttribute(clahe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
     ctx->attrs_set = true;
     return NV12EQ_OK;
 }
@@ -349,7 +349,7 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     if (ws.gw != w || ws.gh != h || ws.gtx != tx || ws.gty != ty || !ws.cells.p) {
         std::vector<int4> xc, yc;
         axis_cells(w, g.inv_tw, tx, 1024, 8, xc);
-        axis_cells(h, g.inv_th, ty, 512, 1, yc);
+        axis_cells(h, g.inv_th, ty, kMaxCellRows, 1, yc);
         rc = dev_reserve(ctx, ws.cells, (xc.size() + yc.size()) * sizeof(int4), false);
         if (rc) return rc;
         // stream-ordered after any kernel still reading the previous tables; the pageable source makes the call
@@ -408,8 +408,8 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
         p.trace = reinterpret_cast<unsigned long long*>(trace_buf.p);
     }
     const int grid = grid_for(ctx, items, 2);
-    if (per_sm <= 1) clahe_kernel<1><<<grid, kThreads, kLaneTableBytes, st>>>(p);
-    else clahe_kernel<2><<<grid, kThreads, kLaneTableBytes, st>>>(p);
+    if (per_sm <= 1) clahe_kernel<1><<<grid, kThreads, kClaheSmemBytes, st>>>(p);
+    else clahe_kernel<2><<<grid, kThreads, kClaheSmemBytes, st>>>(p);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
     if (trace_path) {
