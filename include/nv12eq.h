@@ -20,6 +20,11 @@
  *   nv12eq_color_equalize / _clahe      <- cvtColor(BGR2YUV) -> split -> equalizeHist/CLAHE(Y) -> merge ->
  *                                          cvtColor(YUV2BGR), singlecolor.cpp:39-66, clahe1frame.cpp:83-102
  *   nv12eq_get_counters                 <- the Counters struct + status tick, OpenCLequalHist.cpp:45-61,439-508
+ *   nv12eq_stream_*                     <- the frame queue between capture and encoder: GAsyncQueue + worker threads
+ *                                          (OpenCVequalHist.cpp:71-98,102-196,397-402) with the leaky queues around them
+ *                                          (leaky=downstream max-size-buffers=8 / drop=true, :296-297,:312), plus the
+ *                                          in-order output the reference's unpublished IMP/improvement binaries added
+ *                                          ("frame-output-ordering", "Max reorder", "Dropped: late/backpressure")
  *
  * Conventions:
  *   - every function returns an nv12eq_status (0 = ok); nothing throws, aborts or exits.  A failed frame is
@@ -61,7 +66,10 @@ typedef enum nv12eq_status {
     NV12EQ_ERR_NO_DEVICE = 4,        /* no CUDA device / wrong architecture (needs sm_100) */
     NV12EQ_ERR_OUT_OF_MEMORY = 5,
     NV12EQ_ERR_BAD_SLOT = 6,         /* slot index out of range, or slot busy / not submitted */
-    NV12EQ_ERR_TOO_LARGE = 7         /* frame exceeds the max_width/max_height given to nv12eq_create, or 2^31 pixels */
+    NV12EQ_ERR_TOO_LARGE = 7,        /* frame exceeds the max_width/max_height given to nv12eq_create, or 2^31 pixels */
+    NV12EQ_ERR_DROPPED = 8,          /* stream: the frame was dropped by the back-pressure policy (counted, not an error
+                                        for the pipeline: the reference drops too, OpenCVequalHist.cpp:296,312) */
+    NV12EQ_ERR_EMPTY = 9             /* stream: nothing to pop (or the oldest frame is not finished and block == 0) */
 } nv12eq_status;
 
 /* What to put in the output chroma plane. */
@@ -162,6 +170,46 @@ int nv12eq_color_equalize_device(nv12eq_ctx* ctx, const uint8_t* d_bgr_in, uint8
 int nv12eq_color_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_bgr_in, uint8_t* d_bgr_out, int n_frames,
                               size_t frame_pitch, int width, int height, int stride, int color_mode, double clip_limit,
                               int tiles_x, int tiles_y, void* cuda_stream);
+
+/* ---- ordered, back-pressured frame stream -------------------------------- */
+/* A stream is the reference's worker queue as one object: frames are pushed in capture order, run on `depth` slots
+ * (own CUDA stream, pinned staging and device buffers each, so upload / kernel / download of consecutive frames
+ * overlap), and are popped strictly in push order with their sequence number.  One producer thread may push while
+ * one consumer thread pops; the context must not be used for other calls meanwhile. */
+typedef struct nv12eq_stream nv12eq_stream;
+typedef enum nv12eq_op { NV12EQ_OP_EQUALIZE = 0, NV12EQ_OP_CLAHE = 1 } nv12eq_op;
+typedef enum nv12eq_full_policy {
+    NV12EQ_FULL_BLOCK = 0,       /* push waits until the consumer pops (GAsyncQueue without a bound never drops) */
+    NV12EQ_FULL_DROP_NEWEST = 1, /* push returns NV12EQ_ERR_DROPPED and the frame is not processed */
+    NV12EQ_FULL_DROP_OLDEST = 2  /* the oldest undelivered frame is discarded: GStreamer leaky=downstream / drop=true,
+                                    what the reference configures (OpenCVequalHist.cpp:296-297) */
+} nv12eq_full_policy;
+typedef struct nv12eq_stream_config {
+    int op;                 /* nv12eq_op */
+    int width, height, stride;
+    int uv_mode;            /* nv12eq_uv_mode */
+    double clip_limit;      /* CLAHE only */
+    int tiles_x, tiles_y;   /* CLAHE only */
+    int depth;              /* frames in flight, 1..64 (reference: max-size-buffers=8) */
+    int full_policy;        /* nv12eq_full_policy */
+} nv12eq_stream_config;
+typedef struct nv12eq_stream_stats {
+    uint64_t pushed;               /* frames accepted */
+    uint64_t delivered;            /* frames popped */
+    uint64_t dropped_backpressure; /* frames dropped by the full policy (newest or oldest) */
+    uint64_t in_flight;            /* accepted, not yet popped or dropped */
+    uint64_t max_in_flight;
+    uint64_t latency_us_sum;       /* push -> pop wall time of delivered frames */
+    uint64_t latency_us_max;
+} nv12eq_stream_stats;
+int nv12eq_stream_open(nv12eq_ctx* ctx, const nv12eq_stream_config* cfg, nv12eq_stream** out_stream);
+/* Copies the frame (in_size >= stride*(h + h/2)) and queues it.  *out_seq (optional) = its sequence number, 0, 1, ... */
+int nv12eq_stream_push(nv12eq_stream* s, const uint8_t* in, size_t in_size, uint64_t* out_seq);
+/* Oldest undelivered frame -> out; *out_seq = its sequence number (gaps = dropped frames).  block != 0 waits for a
+ * frame to be pushed and finished; block == 0 returns NV12EQ_ERR_EMPTY instead of waiting. */
+int nv12eq_stream_pop(nv12eq_stream* s, uint8_t* out, size_t out_size, uint64_t* out_seq, int block);
+int nv12eq_stream_get_stats(nv12eq_stream* s, nv12eq_stream_stats* out);
+void nv12eq_stream_close(nv12eq_stream* s);
 
 /* ---- synthetic inputs on the device (SURVEY.md Appendix B generator; bench/test utility) --------------- */
 /* Frame k of the batch is synth_nv12(width, height, seed, first_frame + k). */

@@ -26,9 +26,12 @@ LIB_PATH = os.environ.get("NV12EQ_LIB") or os.path.join(_HERE, "libnv12eq.so")  
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nv12eq.h")
 
 # enums of include/nv12eq.h
-OK, ERR_INVALID_ARGUMENT, ERR_SHORT_BUFFER, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_BAD_SLOT, ERR_TOO_LARGE = range(8)
+(OK, ERR_INVALID_ARGUMENT, ERR_SHORT_BUFFER, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_BAD_SLOT, ERR_TOO_LARGE, ERR_DROPPED,
+ ERR_EMPTY) = range(10)
 UV_COPY, UV_GRAY128, UV_SKIP = 0, 1, 2
 COLOR_YUV, COLOR_YCRCB = 0, 1
+OP_EQUALIZE, OP_CLAHE = 0, 1
+FULL_BLOCK, FULL_DROP_NEWEST, FULL_DROP_OLDEST = 0, 1, 2
 
 _u8p = ctypes.POINTER(ctypes.c_uint8)
 _c_int, _c_sz, _c_dbl, _c_vp, _c_u32 = ctypes.c_int, ctypes.c_size_t, ctypes.c_double, ctypes.c_void_p, ctypes.c_uint32
@@ -43,6 +46,17 @@ class Nv12eqError(RuntimeError):
 class Counters(ctypes.Structure):
     _fields_ = [("frames", ctypes.c_uint64), ("bytes_in", ctypes.c_uint64), ("bytes_out", ctypes.c_uint64),
                 ("errors", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("busy_us", ctypes.c_uint64)]
+
+
+class StreamConfig(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_int), ("width", ctypes.c_int), ("height", ctypes.c_int), ("stride", ctypes.c_int),
+                ("uv_mode", ctypes.c_int), ("clip_limit", ctypes.c_double), ("tiles_x", ctypes.c_int), ("tiles_y", ctypes.c_int),
+                ("depth", ctypes.c_int), ("full_policy", ctypes.c_int)]
+
+
+class StreamStats(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_uint64) for k in ("pushed", "delivered", "dropped_backpressure", "in_flight", "max_in_flight",
+                                               "latency_us_sum", "latency_us_max")]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -89,6 +103,11 @@ _SIGNATURES = {
     "nv12eq_color_clahe": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int]),
     "nv12eq_color_equalize_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "nv12eq_color_clahe_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_vp]),
+    "nv12eq_stream_open": (_c_int, [_c_vp, ctypes.POINTER(StreamConfig), ctypes.POINTER(_c_vp)]),
+    "nv12eq_stream_push": (_c_int, [_c_vp, _c_vp, _c_sz, ctypes.POINTER(ctypes.c_uint64)]),
+    "nv12eq_stream_pop": (_c_int, [_c_vp, _c_vp, _c_sz, ctypes.POINTER(ctypes.c_uint64), _c_int]),
+    "nv12eq_stream_get_stats": (_c_int, [_c_vp, ctypes.POINTER(StreamStats)]),
+    "nv12eq_stream_close": (None, [_c_vp]),
     "nv12eq_synth_nv12_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_u32, _c_u32, _c_vp]),
     "nv12eq_synth_bgr_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_u32, _c_vp]),
 }
@@ -378,6 +397,62 @@ class Context:
                                                       first_frame, _stream_ptr(stream)))
 
 
+class Stream:
+    """Ordered, back-pressured frame stream over one context (``nv12eq_stream_*``): the reference's worker queue
+    (OpenCVequalHist.cpp:71-98,397-402) with in-order delivery.  ``push`` returns the frame's sequence number or None
+    when the back-pressure policy dropped it; ``pop`` returns ``(seq, frame)`` or None when nothing is ready."""
+
+    def __init__(self, ctx: Context, width: int, height: int, op: int = OP_EQUALIZE, stride: Optional[int] = None,
+                 uv_mode: int = UV_COPY, clip_limit: float = 2.0, tiles: Tuple[int, int] = (8, 8), depth: int = 8,
+                 full_policy: int = FULL_BLOCK):
+        self._ctx, self._lib = ctx, ctx._lib
+        stride = width if stride is None else stride
+        self.frame_bytes = nv12_frame_bytes(width, height, stride)
+        cfg = StreamConfig(op, width, height, stride, uv_mode, float(clip_limit), int(tiles[0]), int(tiles[1]), depth, full_policy)
+        h = _c_vp()
+        ctx._check(self._lib.nv12eq_stream_open(ctx._h, ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+
+    def push(self, nv12) -> Optional[int]:
+        seq = ctypes.c_uint64()
+        st = self._lib.nv12eq_stream_push(self._h, _ptr(nv12), _nbytes(nv12), ctypes.byref(seq))
+        if st == ERR_DROPPED:
+            return None
+        self._ctx._check(st)
+        return int(seq.value)
+
+    def pop(self, out=None, block: bool = True):
+        out = np.empty(self.frame_bytes, np.uint8) if out is None else out
+        seq = ctypes.c_uint64()
+        st = self._lib.nv12eq_stream_pop(self._h, _ptr(out), _nbytes(out), ctypes.byref(seq), 1 if block else 0)
+        if st == ERR_EMPTY:
+            return None
+        self._ctx._check(st)
+        return int(seq.value), out
+
+    def stats(self) -> dict:
+        s = StreamStats()
+        self._ctx._check(self._lib.nv12eq_stream_get_stats(self._h, ctypes.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in StreamStats._fields_}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nv12eq_stream_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------------------------------------------------
 # Reference-shaped operator interface (names and argument meaning of the OpenCV calls the reference makes)
 # ------------------------------------------------------------------------------------------------------------
@@ -426,3 +501,6 @@ class CLAHE:
 def createCLAHE(clipLimit: float = 40.0, tileGridSize: Sequence[int] = (8, 8), ctx: Optional[Context] = None) -> CLAHE:
     """Same defaults as ``cv::createCLAHE`` (40.0, 8x8); the reference passes 2.0 / 8 (clahevideo.cpp:384-385)."""
     return CLAHE(clipLimit, tileGridSize, ctx)
+
+
+from . import sharding  # noqa: E402  (multi-GPU partitioning helpers: shard_range, Reassembler, FrameShardedStream, ...)

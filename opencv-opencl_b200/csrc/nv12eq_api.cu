@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -630,6 +631,8 @@ const char* nv12eq_status_string(int s) {
         case NV12EQ_ERR_OUT_OF_MEMORY: return "out of memory";
         case NV12EQ_ERR_BAD_SLOT: return "bad or busy slot";
         case NV12EQ_ERR_TOO_LARGE: return "frame too large";
+        case NV12EQ_ERR_DROPPED: return "frame dropped by the back-pressure policy";
+        case NV12EQ_ERR_EMPTY: return "no frame ready";
         default: return "unknown status";
     }
 }
@@ -900,6 +903,199 @@ int nv12eq_color_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_o
                       tiles_y, pick_stream(ctx, cuda_stream));
     if (!rc) ctx->ctr.frames += (uint64_t)n_frames;
     return rc;
+}
+
+
+// ---- ordered, back-pressured frame stream ---------------------------------------------------------------
+// FIFO ring of `depth` lanes.  push() takes the tail lane, pop() the head lane, so delivery order == push order by
+// construction; sequence numbers make drops visible to the consumer.
+}  // extern "C"
+
+struct nv12eq_stream {
+    nv12eq_ctx* ctx = nullptr;
+    nv12eq_stream_config cfg{};
+    size_t frame_bytes = 0;
+    std::vector<Lane> lanes;
+    std::vector<uint64_t> seq;                                   // sequence number held by each lane
+    std::vector<std::chrono::steady_clock::time_point> t_push;   // push time of each lane's frame
+    size_t head = 0, count = 0;                                  // ring state (guarded by mu)
+    uint64_t next_seq = 0;
+    nv12eq_stream_stats st{};
+    std::mutex mu;
+    std::condition_variable cv;
+    std::string last_error;
+};
+
+namespace {
+int stream_fail(nv12eq_stream* s, int status, const char* msg) {
+    if (s) { s->last_error = msg; if (s->ctx) s->ctx->last_error = msg; }
+    return status;
+}
+// Launch one frame on a lane whose pinned input already holds the frame.
+int stream_launch(nv12eq_stream* s, Lane& L) {
+    nv12eq_ctx* ctx = s->ctx;
+    const nv12eq_stream_config& c = s->cfg;
+    uint8_t* d_in = reinterpret_cast<uint8_t*>(L.d_in.p);
+    uint8_t* d_out = reinterpret_cast<uint8_t*>(L.d_out.p);
+    CK(ctx, cudaMemcpyAsync(d_in, L.h_in.p, s->frame_bytes, cudaMemcpyHostToDevice, L.stream));
+    int rc = (c.op == NV12EQ_OP_CLAHE)
+                 ? launch_clahe(ctx, L.ws, d_in, d_out, 1, s->frame_bytes, c.width, c.height, c.stride, c.clip_limit, c.tiles_x,
+                                c.tiles_y, c.uv_mode, L.stream)
+                 : launch_equalize(ctx, L.ws, d_in, d_out, 1, s->frame_bytes, c.width, c.height, c.stride, c.uv_mode, L.stream);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(L.h_out.p, d_out, s->frame_bytes, cudaMemcpyDeviceToHost, L.stream));
+    CK(ctx, cudaEventRecord(L.done, L.stream));
+    return NV12EQ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int nv12eq_stream_open(nv12eq_ctx* ctx, const nv12eq_stream_config* cfg, nv12eq_stream** out_stream) {
+    if (!ctx || !cfg || !out_stream) return NV12EQ_ERR_INVALID_ARGUMENT;
+    *out_stream = nullptr;
+    int rc = check_geometry(ctx, cfg->width, cfg->height, cfg->stride, 1, 0, cfg->uv_mode);
+    if (rc) return rc;
+    if (cfg->op != NV12EQ_OP_EQUALIZE && cfg->op != NV12EQ_OP_CLAHE) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad stream op %d", cfg->op);
+    if (cfg->op == NV12EQ_OP_CLAHE && (cfg->tiles_x < 1 || cfg->tiles_y < 1)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", cfg->tiles_x, cfg->tiles_y);
+    if (cfg->depth < 1 || cfg->depth > 64) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "stream depth %d out of range 1..64", cfg->depth);
+    if (cfg->full_policy < 0 || cfg->full_policy > 2) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad full_policy %d", cfg->full_policy);
+    nv12eq_stream* s = new (std::nothrow) nv12eq_stream();
+    if (!s) return NV12EQ_ERR_OUT_OF_MEMORY;
+    s->ctx = ctx; s->cfg = *cfg;
+    s->frame_bytes = (size_t)cfg->stride * (size_t)(cfg->height + cfg->height / 2);
+    s->lanes.resize(cfg->depth); s->seq.assign(cfg->depth, 0); s->t_push.resize(cfg->depth);
+    DeviceGuard guard(ctx->device);
+    // With UV_SKIP or strided frames some output bytes are never written by the kernels: start them at zero.
+    for (auto& L : s->lanes) {
+        bool ok = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) == cudaSuccess;
+        if (ok) rc = dev_reserve(ctx, L.d_in, s->frame_bytes, false);
+        if (ok && !rc) rc = dev_reserve(ctx, L.d_out, s->frame_bytes, true);
+        if (ok && !rc) rc = host_reserve(ctx, L.h_in, s->frame_bytes);
+        if (ok && !rc) rc = host_reserve(ctx, L.h_out, s->frame_bytes);
+        if (!ok || rc) {
+            if (!rc) rc = fail(ctx, NV12EQ_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            nv12eq_stream_close(s);
+            return rc;
+        }
+    }
+    *out_stream = s;
+    return NV12EQ_OK;
+}
+
+int nv12eq_stream_push(nv12eq_stream* s, const uint8_t* in, size_t in_size, uint64_t* out_seq) {
+    if (!s || !in) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (in_size < s->frame_bytes) return stream_fail(s, NV12EQ_ERR_SHORT_BUFFER, "stream push: buffer smaller than the frame");
+    DeviceGuard guard(s->ctx->device);
+    const size_t depth = s->lanes.size();
+    std::unique_lock<std::mutex> lk(s->mu);
+    if (s->count == depth) {
+        switch (s->cfg.full_policy) {
+            case NV12EQ_FULL_DROP_NEWEST:
+                s->st.dropped_backpressure++;
+                if (out_seq) *out_seq = s->next_seq;
+                s->next_seq++;  // the dropped frame keeps its number: the consumer sees a gap
+                return NV12EQ_ERR_DROPPED;
+            case NV12EQ_FULL_DROP_OLDEST: {
+                Lane& old = s->lanes[s->head];
+                lk.unlock();
+                cudaEventSynchronize(old.done);  // its GPU work has to leave the lane before the lane is reused
+                lk.lock();
+                if (s->count == depth) {         // the consumer may have popped it meanwhile
+                    s->head = (s->head + 1) % depth;
+                    s->count--;
+                    s->st.dropped_backpressure++;
+                }
+                break;
+            }
+            default:
+                s->cv.wait(lk, [&] { return s->count < depth; });
+        }
+    }
+    const size_t tail = (s->head + s->count) % depth;
+    Lane& L = s->lanes[tail];
+    lk.unlock();
+    // the tail lane is free (not in [head, head+count)) and only the producer touches free lanes
+    memcpy(L.h_in.p, in, s->frame_bytes);
+    const auto now = std::chrono::steady_clock::now();
+    int rc = stream_launch(s, L);
+    if (rc) return rc;
+    lk.lock();
+    const uint64_t q = s->next_seq++;
+    s->seq[tail] = q;
+    s->t_push[tail] = now;
+    s->count++;
+    s->st.pushed++;
+    s->st.in_flight = s->count;
+    s->st.max_in_flight = std::max<uint64_t>(s->st.max_in_flight, s->count);
+    if (out_seq) *out_seq = q;
+    lk.unlock();
+    s->cv.notify_all();
+    return NV12EQ_OK;
+}
+
+int nv12eq_stream_pop(nv12eq_stream* s, uint8_t* out, size_t out_size, uint64_t* out_seq, int block) {
+    if (!s || !out) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (out_size < s->frame_bytes) return stream_fail(s, NV12EQ_ERR_SHORT_BUFFER, "stream pop: buffer smaller than the frame");
+    DeviceGuard guard(s->ctx->device);
+    const size_t depth = s->lanes.size();
+    std::unique_lock<std::mutex> lk(s->mu);
+    if (s->count == 0) {
+        if (!block) return NV12EQ_ERR_EMPTY;
+        s->cv.wait(lk, [&] { return s->count > 0; });
+    }
+    const size_t h = s->head;
+    Lane& L = s->lanes[h];
+    const uint64_t q = s->seq[h];
+    lk.unlock();
+    if (block) {
+        cudaError_t e = cudaEventSynchronize(L.done);
+        if (e != cudaSuccess) return stream_fail(s, NV12EQ_ERR_CUDA, cudaGetErrorString(e));
+    } else {
+        cudaError_t e = cudaEventQuery(L.done);
+        if (e == cudaErrorNotReady) { cudaGetLastError(); return NV12EQ_ERR_EMPTY; }
+        if (e != cudaSuccess) return stream_fail(s, NV12EQ_ERR_CUDA, cudaGetErrorString(e));
+    }
+    lk.lock();
+    if (s->head != h || s->count == 0 || s->seq[h] != q) {
+        // DROP_OLDEST discarded this frame while we were waiting for it: try again with the new head
+        lk.unlock();
+        return nv12eq_stream_pop(s, out, out_size, out_seq, block);
+    }
+    // copy out under the lock: a DROP_OLDEST producer must not recycle the lane while it is being read
+    memcpy(out, L.h_out.p, s->frame_bytes);
+    const uint64_t us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - s->t_push[h]).count();
+    s->head = (s->head + 1) % depth;
+    s->count--;
+    s->st.delivered++;
+    s->st.in_flight = s->count;
+    s->st.latency_us_sum += us;
+    s->st.latency_us_max = std::max(s->st.latency_us_max, us);
+    if (out_seq) *out_seq = q;
+    lk.unlock();
+    s->cv.notify_all();
+    return NV12EQ_OK;
+}
+
+int nv12eq_stream_get_stats(nv12eq_stream* s, nv12eq_stream_stats* out) {
+    if (!s || !out) return NV12EQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(s->mu);
+    *out = s->st;
+    return NV12EQ_OK;
+}
+
+void nv12eq_stream_close(nv12eq_stream* s) {
+    if (!s) return;
+    DeviceGuard guard(s->ctx->device);
+    for (auto& L : s->lanes) {
+        if (L.stream) cudaStreamSynchronize(L.stream);
+        dev_release(L.d_in); dev_release(L.d_out); host_release(L.h_in); host_release(L.h_out);
+        ws_release(L.ws);
+        if (L.done) cudaEventDestroy(L.done);
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
+    delete s;
 }
 
 // ---- synthetic inputs -----------------------------------------------------------------------------------

@@ -128,6 +128,24 @@ def c_equalize_hist(y: np.ndarray) -> np.ndarray:
     return out
 
 
+def c_hist256(y: np.ndarray) -> np.ndarray:
+    """256-bin int32 histogram of a 2-D uint8 plane (a2.1)."""
+    y = np.ascontiguousarray(y)
+    H, W = y.shape
+    hist = np.zeros(256, dtype=np.int32)
+    lib().oracle_hist256(_p(y), W, W, H, hist.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    return hist
+
+
+def c_equalize_lut(hist: np.ndarray, total: int) -> np.ndarray:
+    """equalizeHist LUT of a 256-bin histogram describing `total` pixels (a2.2).  For a constant image every entry that
+    can be read equals the constant."""
+    hist = np.ascontiguousarray(hist, dtype=np.int32)
+    lut = np.zeros(256, dtype=np.uint8)
+    lib().oracle_equalize_lut(hist.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(total), _p(lut))
+    return lut
+
+
 def c_clahe(y: np.ndarray, clip=2.0, tx=8, ty=8) -> np.ndarray:
     y = np.ascontiguousarray(y)
     H, W = y.shape

@@ -60,6 +60,21 @@ def test_library_is_sm100a_only(nv):
     assert archs == {"100a"}, archs
 
 
+def test_no_contracted_float_arithmetic(nv):
+    """OpenCV's CLAHE blend rounds every product and sum separately; a fused multiply-add anywhere in
+    the library would round once instead of twice.  ptxas is known to contract mul.rn.f32x2 + add.rn.f32x2 into FFMA2,
+    so the build is checked: no FFMA2 anywhere, and no FFMA at all inside the CLAHE kernels (integer IMAD is fine; the
+    scalar FFMAs in equalize_kernel are the Newton steps of the correctly rounded __fdiv_rn(255, total - hist[i0]))."""
+    sass = subprocess.run(["cuobjdump", "-sass", nv.LIB_PATH], capture_output=True, text=True).stdout
+    assert "clahe_kernel" in sass
+    assert not re.findall(r"\bFFMA2\b[^;]*;", sass)
+    for fn in re.split(r"\n\s*Function : ", sass)[1:]:
+        if "clahe_kernel" in fn.splitlines()[0]:
+            fused = re.findall(r"\bFFMA\b[^;]*;", fn)
+            assert not fused, fused[:4]
+    assert "FMUL2" in sass and "FADD2.FTZ" in sass  # the packed, unfused blend is what was built
+
+
 def test_no_device_fails_loudly(nv):
     import torch
     if torch.cuda.is_available():
