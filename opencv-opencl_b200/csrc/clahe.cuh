@@ -36,11 +36,33 @@ namespace nv12eq {
 
 constexpr int kMaxCells = 4096;  // per axis (tiles + 1); plenty
 constexpr int kMaxCellRows = 512;               // rows per interpolation cell (host cuts longer runs)
-constexpr int kRowTableBytes = 256 * 256;       // 256 rows of 256 bytes: hist[bin][32 lanes] u32 or table[v][32 lanes] uint2
+// CTA shape of clahe_kernel (compile-time; the Makefile's EXTRA can override for experiments):
+//   256 threads x 4 CTAs/SM with 128-byte table rows (32 KB table) -- the default: four independent items per SM fill the
+//       bubbles of the per-item phases (table build, LUT warp, barriers); measured 8.1 us vs 9.1 us per 4K frame and
+//       2.6 us vs 3.6 us per 1080p frame against
+//   512 threads x 2 CTAs/SM with 256-byte table rows (one-PRMT addressing, 64 KB table).
+#ifndef NV12EQ_CLAHE_THREADS
+#define NV12EQ_CLAHE_THREADS 256
+#endif
+#ifndef NV12EQ_CLAHE_ROWSHIFT
+#define NV12EQ_CLAHE_ROWSHIFT 7
+#endif
+#ifndef NV12EQ_CLAHE_CTAS
+#define NV12EQ_CLAHE_CTAS 4
+#endif
+constexpr int kCT = NV12EQ_CLAHE_THREADS;       // threads per CTA
+constexpr int kCWarps = kCT / 32;
+constexpr int kClaheCtas = NV12EQ_CLAHE_CTAS;   // CTAs per SM the kernel is built for
+constexpr int kRowShift = NV12EQ_CLAHE_ROWSHIFT;
+constexpr int kRowBytes = 1 << kRowShift;       // bytes per table row: hist[bin][32 lanes] u32 (128 B used) or table[v][reps] uint2
+constexpr int kCellReps = kRowBytes / 8;        // 8-byte replicas of a cell table entry (32 or 16: conflict-free per half-warp)
+static_assert(kRowShift == 7 || kRowShift == 8, "table rows are 128 or 256 bytes");
+static_assert(kCT % 256 == 0 && kCT >= 256 && kCT <= 1024, "table build maps threads to the 256 values");
+constexpr int kRowTableBytes = 256 * kRowBytes;
 constexpr int kRingDepth = 8;                   // pixel rows in flight per thread in the cell loop (power of two)
 constexpr int kTileDepth = 4;                   // 16-byte tile row pieces in flight per thread in the tile loop
-constexpr int kRingBytes = kRingDepth * kThreads * 8;
-static_assert(kTileDepth * kThreads * 16 <= kRingBytes, "tile ring must fit");
+constexpr int kRingBytes = kRingDepth * kCT * 8;
+static_assert(kTileDepth * kCT * 16 <= kRingBytes, "tile ring must fit");
 constexpr int kClaheSmemBytes = kRowTableBytes + kRingBytes;  // dynamic shared memory of clahe_kernel
 
 struct ClaheParams {
@@ -69,6 +91,7 @@ struct ClaheParams {
     uint32_t* ticket;      // [1] self-cleaned
     uint32_t* status;      // [1]
     unsigned long long* trace;  // optional [items][4] (developer tool)
+    int debug_skip;             // developer tool: bit0 skip tile histogram, bit1 skip cell blend, bit2 skip uv, bit3 skip LUT warp, bit4 skip table build
 };
 
 __device__ __forceinline__ int reflect101(int p, int len) {
@@ -78,18 +101,22 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 }
 
 // ---- 256-byte-row shared tables -----------------------------------------------------------------------------
-// Row v of the table starts at tbase + v*256.  `lane_off` is this lane's byte offset inside a row (< 256, so it
-// lives in byte 0 of the register); byte K of a packed pixel word goes to byte 1: one PRMT = the whole offset.
+// Row v of the table starts at tbase + v*kRowBytes.  `lane_off` is this lane's byte offset inside a row.  With 256-byte
+// rows it lives in byte 0 of the register and byte K of a packed pixel word goes to byte 1: one PRMT = the whole offset.
+// With 128-byte rows it is PRMT (extract) + one multiply-add onto the loop-invariant tbase + lane_off.
 template <int K>
-__device__ __forceinline__ uint32_t row_entry(uint32_t w, uint32_t lane_off) { return __byte_perm(w, lane_off, 0x5504u | (K << 4)); }
+__device__ __forceinline__ uint32_t row_addr(uint32_t w, uint32_t tbase, uint32_t lane_off) {
+    if (kRowShift == 8) return tbase + __byte_perm(w, lane_off, 0x5504u | (K << 4));
+    return (tbase + lane_off) + (byte_of<K>(w) << kRowShift);
+}
 
 // histogram rows: hist[bin][lane] u32 in the first 128 bytes of row `bin`
-__device__ __forceinline__ void hist256_byte(uint32_t v, uint32_t tbase, uint32_t lane4) { red_shared_inc(tbase + (v << 8) + lane4); }
+__device__ __forceinline__ void hist256_byte(uint32_t v, uint32_t tbase, uint32_t lane4) { red_shared_inc(tbase + (v << kRowShift) + lane4); }
 __device__ __forceinline__ void hist256_word(uint32_t w, uint32_t tbase, uint32_t lane4) {
-    red_shared_inc(tbase + row_entry<0>(w, lane4));
-    red_shared_inc(tbase + row_entry<1>(w, lane4));
-    red_shared_inc(tbase + row_entry<2>(w, lane4));
-    red_shared_inc(tbase + row_entry<3>(w, lane4));
+    red_shared_inc(row_addr<0>(w, tbase, lane4));
+    red_shared_inc(row_addr<1>(w, tbase, lane4));
+    red_shared_inc(row_addr<2>(w, tbase, lane4));
+    red_shared_inc(row_addr<3>(w, tbase, lane4));
 }
 __device__ __forceinline__ void hist256_vec(int4 v, uint32_t tbase, uint32_t lane4) {
     hist256_word((uint32_t)v.x, tbase, lane4);
@@ -111,13 +138,13 @@ __device__ __forceinline__ void hist256_span_warp(const uint8_t* __restrict__ p,
 __device__ __forceinline__ void hist256_zero(uint32_t* tab) {
     const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int k = 0; k < 2048 / kThreads; ++k) {
-        const int i = threadIdx.x + k * kThreads;  // 16-byte slot i of the used halves: row i>>3, column i&7
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(tab) + (i >> 3) * 256 + (i & 7) * 16) = z;
+    for (int k = 0; k < 2048 / kCT; ++k) {
+        const int i = threadIdx.x + k * kCT;  // 16-byte slot i of the 128 counter bytes of every row: row i>>3, column i&7
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(tab) + (i >> 3) * kRowBytes + (i & 7) * 16) = z;
     }
 }
 __device__ __forceinline__ uint32_t hist256_row_sum(const uint32_t* tab, int bin) {
-    const uint8_t* row = reinterpret_cast<const uint8_t*>(tab) + bin * 256;
+    const uint8_t* row = reinterpret_cast<const uint8_t*>(tab) + bin * kRowBytes;
     uint32_t s = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -190,7 +217,7 @@ __device__ __forceinline__ float clahe_blend_res(uint2 e, float xa, float xa1, u
 }
 template <int K>
 __device__ __forceinline__ float clahe_blend_px(uint32_t w, uint32_t tbase, uint32_t lane8, float xa, float xa1, uint64_t yw) {
-    return clahe_blend_res(lds_u64(tbase + row_entry<K>(w, lane8)), xa, xa1, yw);
+    return clahe_blend_res(lds_u64(row_addr<K>(w, tbase, lane8)), xa, xa1, yw);
 }
 __device__ __forceinline__ void round_pair(float a, float b, uint32_t& oa, uint32_t& ob) {
     unpack_u2(add_f2(pack_f2(a, b), pack_f2(12582912.0f, 12582912.0f)), oa, ob);
@@ -229,7 +256,7 @@ __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float&
 __device__ __forceinline__ void pin_register(float& v) { asm volatile("" : "+f"(v)); }
 
 template <int MIN_CTAS>
-__global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClaheParams p) {
+__global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams p) {
     uint32_t* const smem_rows = nv12eq_smem_rows;  // 64 KB of 256-byte rows: hist[bin][32] (tile items) / table[v][32] (cells); then the ring
     __shared__ uint32_t s_bins[256];
     __shared__ __align__(8) float2 s_yw[kMaxCellRows];  // (ya1, ya) of the rows of the current cell
@@ -245,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
     uint32_t tbase;
     asm("mov.u32 %0, nv12eq_smem_rows;" : "=r"(tbase));
     const uint32_t rbase = tbase + kRowTableBytes;  // cp.async ring of the cell loop
-    const uint32_t lane4 = (uint32_t)lane * 4u, lane8 = (uint32_t)lane * 8u;
+    const uint32_t lane4 = (uint32_t)lane * 4u, lane8 = (uint32_t)(lane & (kCellReps - 1)) * 8u;
 
     TicketQueue q{p.ticket, s_ticket, 0u, 0u, false};
     q.start();
@@ -270,29 +297,30 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 __syncthreads();
                 const uint64_t keep = l2_policy_evict_last();
                 const bool vec_ok = !p.padded && (p.tw & 15) == 0 && (p.stride & 15) == 0 &&
-                                    (((uintptr_t)y + (uintptr_t)x0) & 15) == 0 && (p.tw >> 4) <= kThreads;
-                if (vec_ok) {
+                                    (((uintptr_t)y + (uintptr_t)x0) & 15) == 0 && (p.tw >> 4) <= kCT;
+                if (p.debug_skip & 1) {
+                } else if (vec_ok) {
                     // threads form a (rows_per_pass x vectors_per_row) grid over the tile.  Every thread keeps
                     // kTileDepth-1 of its 16-byte row pieces in flight through a private cp.async ring (64 KB per SM).
                     const int vpr = p.tw >> 4;
-                    const int rpp = kThreads / vpr;
+                    const int rpp = kCT / vpr;
                     const int tr = tid / vpr, tc = tid - tr * vpr;
                     if (tr < rpp && tr < p.th) {
                         const uint8_t* ptr = y + (size_t)(y0 + tr) * p.stride + x0 + tc * 16;
                         const size_t rstep = (size_t)rpp * p.stride;
                         const int nrows = (p.th - tr + rpp - 1) / rpp;
                         const uint32_t ring0 = rbase + (uint32_t)tid * 16u;
-                        constexpr uint32_t kSlot = kThreads * 16u, kRingMask = kTileDepth * kSlot - 1u;
+                        constexpr uint32_t kSlot = kCT * 16u, kRingMask = kTileDepth * kSlot - 1u;
 #pragma unroll
                         for (int j = 0; j < kTileDepth - 1; ++j) {
-                            if (j < nrows) cp_async16_hint(ring0 + (uint32_t)j * kSlot, ptr + (size_t)j * rstep, keep);
+                            if (j < nrows) cp_async16(ring0 + (uint32_t)j * kSlot, ptr + (size_t)j * rstep);
                             cp_async_commit();
                         }
                         const uint8_t* pn = ptr + (size_t)(kTileDepth - 1) * rstep;
                         uint32_t rd = 0u, wr = (uint32_t)(kTileDepth - 1) * kSlot;
 #pragma unroll 1
                         for (int i = 0; i < nrows; ++i) {
-                            if (i + kTileDepth - 1 < nrows) cp_async16_hint(ring0 + wr, pn, keep);
+                            if (i + kTileDepth - 1 < nrows) cp_async16(ring0 + wr, pn);
                             cp_async_commit();
                             cp_async_wait<kTileDepth - 1>();
                             hist256_vec(lds_s4(ring0 + rd), tbase, lane4);
@@ -303,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                     }
                 } else {
                     // general path: one warp per tile row, byte spans inside the image, reflected reads outside
-                    for (int row = warp; row < p.th; row += kWarps) {
+                    for (int row = warp; row < p.th; row += kCWarps) {
                         const uint8_t* src_row = y + (size_t)reflect101(y0 + row, p.h) * p.stride;
                         const int xin = min(x0 + p.tw, p.w);  // end of the in-image part
                         if (x0 < xin) hist256_span_warp(src_row + x0, xin - x0, lane, tbase, lane4, keep);
@@ -316,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 if (tid < 256) s_bins[tid] = hist256_row_sum(smem_rows, tid);
                 __syncthreads();
                 if (warp == 0) {
-                    clahe_tile_lut_warp(s_bins, p.clip_limit, p.lut_scale, p.luts + ((size_t)g * T + r) * 256, lane);
+                    if (!(p.debug_skip & 8)) clahe_tile_lut_warp(s_bins, p.clip_limit, p.lut_scale, p.luts + ((size_t)g * T + r) * 256, lane);
                     __threadfence();
                     __syncwarp();
                     if (lane == 0) atomicAdd(p.tiles_done + g, 1u);
@@ -332,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 const int4 xc = p.xcells[cx], yc = p.ycells[cy];
                 const int cw = xc.y - xc.x, ch = yc.y - yc.x;  // cell size in pixels (ch <= kMaxCellRows)
                 // y weights of the cell's rows (does not depend on the tile LUTs: done before the dependency wait)
-                for (int i = tid; i < ch; i += kThreads) {
+                for (int i = tid; i < ch; i += kCT) {
                     float ya, ya1;
                     axis_weight(yc.x + i, p.inv_th, ya, ya1);
                     s_yw[i] = make_float2(ya1, ya);
@@ -354,9 +382,10 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 __syncthreads();
                 if (!s_flag) break;
                 tr_.mark(item, 1);
+                if (!(p.debug_skip & 16))
                 // pack the four LUTs: row v = 32 lane replicas of {bf16 L11 | L21 << 16, bf16 L12 | L22 << 16}
                 {
-                    constexpr int kShare = kThreads / 256, kPer = 32 / kShare;
+                    constexpr int kShare = kCT / 256, kPer = kCellReps / kShare;
                     const uint8_t* L = p.luts + (size_t)f * T * 256;
                     const int v = tid & 255, part = tid >> 8;
                     const uint32_t l11 = __ldcg(L + (size_t)(yc.z * p.tx + xc.z) * 256 + v);
@@ -366,9 +395,9 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                     uint2 e;
                     e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l21) & 0xffff0000u);
                     e.y = (__float_as_uint((float)l12) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
-                    uint2* row = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(smem_rows) + v * 256);
+                    uint2* row = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(smem_rows) + v * kRowBytes);
 #pragma unroll
-                    for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & 31] = e;
+                    for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & (kCellReps - 1)] = e;
                 }
                 __syncthreads();
                 const uint32_t ywbase = smem_u32(s_yw);
@@ -376,18 +405,17 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                 // width is not a multiple of 8 (and everything when alignment does not allow 8-byte accesses) take the
                 // pixel-at-a-time path below.
                 const bool fast = ((xc.x & 7) == 0) && ((p.stride & 7) == 0) && ((((uintptr_t)src | (uintptr_t)dst) & 7) == 0) &&
-                                  (cw >> 3) >= 1 && (cw >> 3) <= kThreads;
+                                  (cw >> 3) >= 1 && (cw >> 3) <= kCT;
                 const int gpr = fast ? (cw >> 3) : 0;   // 8-pixel groups per row
                 const int xslow = xc.x + gpr * 8;        // first column of the pixel-at-a-time path
-                if (fast) {
-                    const int rpp = kThreads / gpr;
+                if (fast && !(p.debug_skip & 2)) {
+                    const int rpp = kCT / gpr;
                     const int tr = tid / gpr, tc = tid - tr * gpr;
                     const int xg = xc.x + tc * 8;
                     if (tr < rpp && tr < ch) {
                         float xa[8], xa1[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) axis_weight(xg + k, p.inv_tw, xa[k], xa1[k]);
-                        const uint64_t once = l2_policy_evict_first();
                         const size_t rstep = (size_t)rpp * p.stride;
                         const int nrows = (ch - tr + rpp - 1) / rpp;  // rows of this thread: tr, tr + rpp, ...
                         const uint8_t* sp = src + (size_t)(yc.x + tr) * p.stride + xg;
@@ -398,10 +426,10 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                         // kRingDepth-1 ahead are in flight (about 60 KB per SM) without holding registers, and since a
                         // thread only ever reads its own slots no barrier is involved.
                         const uint32_t ring0 = rbase + (uint32_t)tid * 8u;
-                        constexpr uint32_t kSlot = kThreads * 8u, kRingMask = kRingDepth * kSlot - 1u;
+                        constexpr uint32_t kSlot = kCT * 8u, kRingMask = kRingDepth * kSlot - 1u;
 #pragma unroll
                         for (int j = 0; j < kRingDepth - 1; ++j) {
-                            if (j < nrows) cp_async8_hint(ring0 + (uint32_t)j * kSlot, sp + (size_t)j * rstep, once);
+                            if (j < nrows) cp_async8(ring0 + (uint32_t)j * kSlot, sp + (size_t)j * rstep);
                             cp_async_commit();
                         }
                         const uint8_t* spn = sp + (size_t)(kRingDepth - 1) * rstep;
@@ -414,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                             const int iend = pass ? nrows : max(nrows - 4, 0);
 #pragma unroll 1
                             for (; i < iend; ++i) {
-                                if (i + kRingDepth - 1 < nrows) cp_async8_hint(ring0 + wr, spn, once);
+                                if (i + kRingDepth - 1 < nrows) cp_async8(ring0 + wr, spn);
                                 cp_async_commit();
                                 cp_async_wait<kRingDepth - 1>();
                                 const uint2 px = lds_u64(ring0 + rd);
@@ -429,39 +457,41 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
                         }
                     }
                 }
-                if (xslow < xc.y) {
+                if (xslow < xc.y && !(p.debug_skip & 2)) {
                     // pixel-at-a-time path
                     const int sw = xc.y - xslow;
                     const long long npix = (long long)sw * ch;
-                    for (long long i = tid; i < npix; i += kThreads) {
+                    for (long long i = tid; i < npix; i += kCT) {
                         const int ry = (int)(i / sw), rx = (int)(i - (long long)ry * sw);
                         const int x = xslow + rx, yy = yc.x + ry;
                         float xa, xa1;
                         axis_weight(x, p.inv_tw, xa, xa1);
                         const uint32_t v = src[(size_t)yy * p.stride + x];
-                        const float res = clahe_blend_res(lds_u64(tbase + (v << 8) + lane8), xa, xa1, lds_b64(ywbase + (uint32_t)ry * 8u));
+                        const float res = clahe_blend_res(lds_u64(tbase + (v << kRowShift) + lane8), xa, xa1, lds_b64(ywbase + (uint32_t)ry * 8u));
                         dst[(size_t)yy * p.stride + x] = (uint8_t)__float_as_uint(__fadd_rn(res, 12582912.0f));
                     }
                 }
             } else {
                 // ------------------------- uv item -------------------------
                 q.prefetch();  // short item: draw the next ticket right away
+                if (!(p.debug_skip & 4)) {
                 const int c = r - T - I;
                 const bool copy_uv = p.uv_mode == UV_COPY && src != dst;
                 const size_t uv_off = (size_t)p.stride * p.h;
                 if (p.flat) {
                     const unsigned long long b0 = min((unsigned long long)c * p.uv_chunk, p.uv_bytes);
                     const unsigned long long b1 = min(b0 + p.uv_chunk, p.uv_bytes);
-                    if (copy_uv) copy_span(src + uv_off + b0, dst + uv_off + b0, (size_t)(b1 - b0), tid, kThreads);
-                    else if (p.uv_mode == UV_GRAY128) fill_span(dst + uv_off + b0, (size_t)(b1 - b0), tid, kThreads, 128);
+                    if (copy_uv) copy_span(src + uv_off + b0, dst + uv_off + b0, (size_t)(b1 - b0), tid, kCT);
+                    else if (p.uv_mode == UV_GRAY128) fill_span(dst + uv_off + b0, (size_t)(b1 - b0), tid, kCT, 128);
                 } else {
                     const int rows = p.h / 2;
                     const int r0 = min(c * p.uv_rows_chunk, rows), r1 = min(r0 + p.uv_rows_chunk, rows);
-                    for (int row = r0 + warp; row < r1; row += kWarps) {
+                    for (int row = r0 + warp; row < r1; row += kCWarps) {
                         const size_t off = uv_off + (size_t)row * p.stride;
                         if (copy_uv) copy_span(src + off, dst + off, (size_t)p.w, lane, 32);
                         else if (p.uv_mode == UV_GRAY128) fill_span(dst + off, (size_t)p.w, lane, 32, 128);
                     }
+                }
                 }
             }
         }
@@ -470,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) clahe_kernel(const ClahePa
     }
     // the last CTA out returns the per-frame counters to zero for the next launch
     if (q.finish())
-        for (int i = tid; i < p.n_frames; i += kThreads) p.tiles_done[i] = 0;
+        for (int i = tid; i < p.n_frames; i += kCT) p.tiles_done[i] = 0;
 }
 
 }  // namespace nv12eq

@@ -18,7 +18,14 @@
 
 namespace nv12eq {
 
-constexpr int kThreads = 512;            // threads per CTA of the hot kernels (2 CTAs/SM: 32 warps, 64 registers/thread)
+#ifndef NV12EQ_EQ_THREADS
+#define NV12EQ_EQ_THREADS 512
+#endif
+#ifndef NV12EQ_EQ_CTAS
+#define NV12EQ_EQ_CTAS 2
+#endif
+constexpr int kEqCtas = NV12EQ_EQ_CTAS;  // CTAs per SM equalize_kernel is built for
+constexpr int kThreads = NV12EQ_EQ_THREADS;  // threads per CTA of equalize_kernel (512 x 2 CTAs/SM: 32 warps, 64 registers/thread)
 constexpr int kWarps = kThreads / 32;
 constexpr int kLaneTableWords = 256 * 32; // one [256][32] uint32 table
 constexpr int kLaneTableBytes = kLaneTableWords * 4;
@@ -119,11 +126,15 @@ __device__ __forceinline__ void stg64_hint(void* p, uint2 v, uint64_t pol) {
 // Asynchronous global -> shared copies (LDGSTS): the data never occupies a register while it is in flight, so a
 // thread can keep many rows outstanding.  Groups are per thread: wait_group<N> returns when all but the newest N
 // committed groups of THIS thread have landed -- a thread that only reads its own slots needs no barrier.
-__device__ __forceinline__ void cp_async8_hint(uint32_t saddr, const void* g, uint64_t pol) {
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(saddr), "l"(g), "l"(pol) : "memory");
+// NOTE: no .L2::cache_hint here.  ptxas 12.9 miscompiles a cache-hinted LDGSTS whose shared address it splits into
+// [R + UR + imm]: the emitted instruction names uniform registers that are never written (seen as
+// `LDGSTS.E.64 [R9+UR0+0x8000], desc[UR1][...]` with UR0/UR1 undefined) and the kernel dies with "illegal instruction".
+// Whether the split happens depends on the surrounding code, so the hint is not worth the risk.
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
 }
-__device__ __forceinline__ void cp_async16_hint(uint32_t saddr, const void* g, uint64_t pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "l"(pol) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

@@ -181,8 +181,9 @@ int ensure_attrs(nv12eq_ctx* ctx) {
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(equalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(clahe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
-    CK(ctx, cudaFuncSetAttribute(clahe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
+    CK(ctx, cudaFuncSetAttribute(clahe_kernel<kClaheCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
     ctx->attrs_set = true;
     return NV12EQ_OK;
 }
@@ -224,7 +225,7 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
     p.uv_bytes = (unsigned long long)w * (h / 2);
     p.total_px = total_px ? total_px : (long long)w * h;
 
-    const int per_sm = ctx->tune_ctas > 0 ? std::min(ctx->tune_ctas, 3) : 2;
+    const int per_sm = ctx->tune_ctas > 0 ? std::min(ctx->tune_ctas, 4) : kEqCtas;
     // chunks per frame: ~128 KB of luma per item, but never fewer items than ~2 waves of CTAs
     const int ctas = ctx->sm_count * per_sm;
     long long C = (long long)((p.y_bytes + 131071) / 131072);
@@ -262,10 +263,11 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
         p.phases = phases;
         const bool both = (phases & PH_HIST) && (phases & PH_APPLY);
         long long items = (long long)(n + (both ? p.lag : 0)) * 2 * C;
-        int grid = grid_for(ctx, items, 2);
+        int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * per_sm, items));
         if (per_sm <= 1) equalize_kernel<1><<<grid, kThreads, smem, st>>>(p);
         else if (per_sm == 2) equalize_kernel<2><<<grid, kThreads, smem, st>>>(p);
-        else equalize_kernel<3><<<grid, kThreads, smem, st>>>(p);
+        else if (per_sm == 3) equalize_kernel<3><<<grid, kThreads, smem, st>>>(p);
+        else equalize_kernel<4><<<grid, kThreads, smem, st>>>(p);
         ctx->ctr.kernel_launches++;
         CK(ctx, cudaGetLastError());
         return NV12EQ_OK;
@@ -385,9 +387,10 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     p.tiles_done = ws_counter(ws, 0);
     p.ticket = ws_ticket(ws);
     p.status = ws_status(ws);
+    if (const char* dbg = getenv("NV12EQ_DEBUG_SKIP")) p.debug_skip = atoi(dbg);
 
     const long long per_slot = (long long)T + (long long)p.nxc * p.nyc + U;
-    const int per_sm = ctx->tune_ctas > 0 ? std::min(ctx->tune_ctas, 2) : 2;
+    const int per_sm = ctx->tune_ctas > 0 ? std::min(ctx->tune_ctas, kClaheCtas) : kClaheCtas;
     {
         // same reasoning as for equalizeHist; tile items run ~1.5x longer than the average item
         const long long grid_ctas = (long long)ctx->sm_count * per_sm;
@@ -408,9 +411,9 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
         if (rc) return rc;
         p.trace = reinterpret_cast<unsigned long long*>(trace_buf.p);
     }
-    const int grid = grid_for(ctx, items, 2);
-    if (per_sm <= 1) clahe_kernel<1><<<grid, kThreads, kClaheSmemBytes, st>>>(p);
-    else clahe_kernel<2><<<grid, kThreads, kClaheSmemBytes, st>>>(p);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * per_sm, items));
+    if (per_sm <= 1) clahe_kernel<1><<<grid, kCT, kClaheSmemBytes, st>>>(p);
+    else clahe_kernel<kClaheCtas><<<grid, kCT, kClaheSmemBytes, st>>>(p);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
     if (trace_path) {
