@@ -310,19 +310,27 @@ def run_ours(args):
         e2e_steps = max(2, min(args.steps, 5))
         host_step()
         barrier()
+        c0 = ctx.counters()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             host_step()
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
+        c1 = ctx.counters()
         ok = True
         if rank == 0:
             ok = bool(np.array_equal(h_out.array[(e2e_n - 1) * pitch:e2e_n * pitch],
                                      d_out[(e2e_n - 1) * pitch:e2e_n * pitch].cpu().numpy()))
-        e2e = {"value": world * e2e_n * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": e2e_n * pitch,
-               "d2h_bytes_per_step": e2e_n * pitch, "frames_per_step": e2e_n, "steps": e2e_steps,
+        # bytes that actually crossed PCIe, from the library's own counters: in passthrough mode only the luma planes
+        # move (W*H of the 1.5*W*H bytes of a frame, each way); the chroma is copied host-to-host by the library's
+        # host threads, as the reference does with memcpy (nextimprovement.cpp:160)
+        e2e = {"value": world * e2e_n * e2e_steps / e2e_s, "unit": "frames/s",
+               "h2d_bytes_per_step": (c1["bytes_in"] - c0["bytes_in"]) // e2e_steps,
+               "d2h_bytes_per_step": (c1["bytes_out"] - c0["bytes_out"]) // e2e_steps,
+               "host_frame_bytes_per_step": e2e_n * pitch, "frames_per_step": e2e_n, "steps": e2e_steps,
                "api": "nv12eq_equalize_hist_batch" if args.op == "equalize" else "nv12eq_clahe_batch",
-               "host_memory": "pinned (nv12eq_host_alloc)", "matches_device_leg": ok}
+               "host_memory": "pinned (nv12eq_host_alloc)", "chroma": "host memcpy inside the call (never crosses PCIe)",
+               "matches_device_leg": ok}
         h_in.free(); h_out.free()
 
     if rank != 0:

@@ -9,10 +9,16 @@
 //   * device-resident entry points use a separate workspace and the caller's stream.
 // There is no CPU implementation anywhere in this library.
 #include <cuda_runtime.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define NV12EQ_HAVE_SSE2 1
+#endif
 
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -66,7 +72,92 @@ struct Workspace {
     int gw = 0, gh = 0, gtx = 0, gty = 0, nxc = 0, nyc = 0;
 };
 
+// Small pool of host threads for the chroma plane of host-buffer calls.  In passthrough mode the chroma bytes never
+// cross PCIe: the GPU only sees the luma planes (8.3 of the 12.4 MB of a 4K frame, each way) while these threads do
+// what the reference does on the CPU anyway, memcpy(out + y_size, in + y_size, uv_size) (nextimprovement.cpp:160) or
+// memset(out + y_size, 128, uv_size) (OpenCVequalHist.cpp:162), concurrently with the DMA and the kernels.
+struct HostTask {
+    uint8_t* dst; const uint8_t* src;   // src == nullptr: fill with `value`
+    int rows; size_t row_bytes, stride; int value;
+    int* pending;                        // counter of the submitting lane, guarded by the pool mutex
+};
+class HostPool {
+public:
+    explicit HostPool(int n) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this] { run(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // Large copies use non-temporal stores: the destination is not read back by this thread, and skipping the
+    // read-for-ownership of every destination line leaves more host memory bandwidth to the PCIe DMA running beside it.
+    static void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+#ifdef NV12EQ_HAVE_SSE2
+        if (n >= (256u << 10)) {
+            const size_t head = (size_t)((16 - ((uintptr_t)dst & 15)) & 15);
+            memcpy(dst, src, head);
+            dst += head; src += head; n -= head;
+            const size_t blocks = n / 64;
+            for (size_t i = 0; i < blocks; ++i, dst += 64, src += 64) {
+                const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src));
+                const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 16));
+                const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 32));
+                const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 48));
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst), a);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 16), b);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 32), c);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 48), d);
+            }
+            _mm_sfence();
+            n -= blocks * 64;
+        }
+#endif
+        memcpy(dst, src, n);
+    }
+    static void execute(const HostTask& t) {
+        for (int r = 0; r < t.rows; ++r) {
+            if (t.src) stream_copy(t.dst + (size_t)r * t.stride, t.src + (size_t)r * t.stride, t.row_bytes);
+            else memset(t.dst + (size_t)r * t.stride, t.value, t.row_bytes);
+        }
+    }
+    void submit(const HostTask& t) {
+        { std::lock_guard<std::mutex> lk(mu_); ++*t.pending; q_.push_back(t); }
+        cv_.notify_one();
+    }
+    void wait(int* pending) {
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return *pending == 0; });
+    }
+private:
+    void run() {
+        for (;;) {
+            HostTask t;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                t = q_.front();
+                q_.pop_front();
+            }
+            execute(t);
+            bool last;
+            { std::lock_guard<std::mutex> lk(mu_); last = (--*t.pending == 0); }
+            if (last) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::deque<HostTask> q_;
+    bool stop_ = false;
+};
+
 struct Lane {
+    int host_pending = 0;                // chroma tasks of this lane still running in the host pool
+    bool luma_only = false;              // pending job moved only the luma planes over PCIe
+    int jw = 0, jh = 0, jstride = 0; size_t jpitch = 0;  // geometry of the pending job (for the pageable-output copy)
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     DevBuf d_in, d_out;
@@ -99,6 +190,8 @@ struct nv12eq_ctx {
     std::string last_error;
     nv12eq_counters ctr{};
     bool attrs_set = false;
+    HostPool* pool = nullptr;   // created on first use by a host-buffer NV12 call
+    int pool_threads = -1;      // -1: decide from the host (NV12EQ_HOST_THREADS overrides), 0: chroma inline on the caller
 };
 
 namespace {
@@ -479,9 +572,103 @@ struct Job {
     double clip; int tx, ty; int color_mode;
 };
 
+// Luma planes of the n frames of a job between two buffers of the job's layout (either side may be the device).
+int copy_luma_async(nv12eq_ctx* ctx, uint8_t* dst, const uint8_t* src, const Job& j, cudaMemcpyKind kind, cudaStream_t st) {
+    if (j.stride == j.w) {  // flat: one luma plane is one contiguous span, frames are `pitch` apart
+        const size_t plane = (size_t)j.w * j.h;
+        if (j.n == 1) { CK(ctx, cudaMemcpyAsync(dst, src, plane, kind, st)); }
+        else { CK(ctx, cudaMemcpy2DAsync(dst, j.pitch, src, j.pitch, plane, (size_t)j.n, kind, st)); }
+    } else {                // strided: only the `w` payload bytes of every row move; padding is never touched
+        for (int k = 0; k < j.n; ++k)
+            CK(ctx, cudaMemcpy2DAsync(dst + (size_t)k * j.pitch, j.stride, src + (size_t)k * j.pitch, j.stride, (size_t)j.w, (size_t)j.h, kind, st));
+    }
+    return NV12EQ_OK;
+}
+void copy_luma_host(uint8_t* dst, const uint8_t* src, int n, size_t pitch, int w, int h, int stride) {
+    for (int k = 0; k < n; ++k) {
+        if (stride == w) memcpy(dst + (size_t)k * pitch, src + (size_t)k * pitch, (size_t)w * h);
+        else for (int r = 0; r < h; ++r) memcpy(dst + (size_t)k * pitch + (size_t)r * stride, src + (size_t)k * pitch + (size_t)r * stride, (size_t)w);
+    }
+}
+size_t luma_payload(const Job& j) { return (size_t)j.n * (size_t)j.w * (size_t)j.h; }
+
+HostPool* host_pool(nv12eq_ctx* ctx) {
+    if (ctx->pool_threads < 0) {
+        int n = (int)std::thread::hardware_concurrency() / 4;
+        if (const char* e = getenv("NV12EQ_HOST_THREADS")) n = atoi(e);
+        ctx->pool_threads = std::max(0, std::min(n, 8));
+    }
+    if (ctx->pool_threads > 0 && !ctx->pool) ctx->pool = new (std::nothrow) HostPool(ctx->pool_threads);
+    return ctx->pool;
+}
+
+// Chroma of a host NV12 job, on the host (see HostPool).  Runs concurrently with the GPU work queued just before.
+void host_chroma(nv12eq_ctx* ctx, Lane& L, const Job& j) {
+    const int rows = j.h / 2;
+    const bool copy = (j.uv_mode == UV_COPY && j.in != j.out);
+    if (rows == 0 || !(copy || j.uv_mode == UV_GRAY128)) return;
+    const size_t off = (size_t)j.stride * j.h;
+    const bool flat = (j.stride == j.w);
+    HostPool* pool = ((size_t)j.n * rows * j.w >= (1u << 20)) ? host_pool(ctx) : nullptr;  // small jobs: inline
+    for (int k = 0; k < j.n; ++k) {
+        HostTask t{};
+        t.dst = j.out + (size_t)k * j.pitch + off;
+        t.src = copy ? j.in + (size_t)k * j.pitch + off : nullptr;
+        t.value = 128;
+        t.rows = flat ? 1 : rows;
+        t.row_bytes = flat ? (size_t)j.w * rows : (size_t)j.w;
+        t.stride = (size_t)j.stride;
+        t.pending = &L.host_pending;
+        if (pool) pool->submit(t); else HostPool::execute(t);
+    }
+}
+
+// Host NV12 frames: only the luma planes cross PCIe, the kernels run with UV_SKIP, the chroma is handled on the host.
+int lane_submit_nv12(nv12eq_ctx* ctx, Lane& L, const Job& j) {
+    const size_t span = (size_t)(j.n - 1) * j.pitch + j.frame_bytes;  // bytes covered in the caller's buffers
+    int rc;
+    if ((rc = dev_reserve(ctx, L.d_in, span, false))) return rc;
+    const bool in_place = (j.in == j.out);
+    if (!in_place && (rc = dev_reserve(ctx, L.d_out, span, false))) return rc;
+    uint8_t* d_in = reinterpret_cast<uint8_t*>(L.d_in.p);
+    uint8_t* d_out = in_place ? d_in : reinterpret_cast<uint8_t*>(L.d_out.p);
+
+    const uint8_t* src = j.in;
+    if (!is_pinned(j.in)) {  // pageable caller memory: stage the luma through pinned memory so the DMA is asynchronous
+        if ((rc = host_reserve(ctx, L.h_in, span))) return rc;
+        copy_luma_host(reinterpret_cast<uint8_t*>(L.h_in.p), j.in, j.n, j.pitch, j.w, j.h, j.stride);
+        src = reinterpret_cast<const uint8_t*>(L.h_in.p);
+    }
+    if ((rc = copy_luma_async(ctx, d_in, src, j, cudaMemcpyHostToDevice, L.stream))) return rc;
+    ctx->ctr.bytes_in += luma_payload(j);
+    if (j.op == Op::Equalize) rc = launch_equalize(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, UV_SKIP, L.stream);
+    else rc = launch_clahe(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.clip, j.tx, j.ty, UV_SKIP, L.stream);
+    if (rc) return rc;
+    uint8_t* dst = j.out;
+    L.user_out = nullptr;
+    if (!is_pinned(j.out)) {
+        if ((rc = host_reserve(ctx, L.h_out, span))) return rc;
+        dst = reinterpret_cast<uint8_t*>(L.h_out.p);
+        L.user_out = j.out;
+    }
+    if ((rc = copy_luma_async(ctx, dst, d_out, j, cudaMemcpyDeviceToHost, L.stream))) return rc;
+    CK(ctx, cudaMemcpyAsync(L.h_status, ws_status(L.ws), sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream));
+    CK(ctx, cudaEventRecord(L.done, L.stream));
+    ctx->ctr.bytes_out += luma_payload(j);
+    host_chroma(ctx, L, j);  // overlaps with the GPU work queued above
+    L.luma_only = true;
+    L.jw = j.w; L.jh = j.h; L.jstride = j.stride; L.jpitch = j.pitch;
+    L.out_bytes = span;
+    L.frames = j.n;
+    L.busy = true;
+    return NV12EQ_OK;
+}
+
 int lane_submit(nv12eq_ctx* ctx, Lane& L, const Job& j) {
     if (L.busy) return fail(ctx, NV12EQ_ERR_BAD_SLOT, "slot is busy; call nv12eq_wait first");
     if (j.n == 0) return NV12EQ_OK;
+    if (j.op == Op::Equalize || j.op == Op::Clahe) return lane_submit_nv12(ctx, L, j);
+    // colour path: whole BGR frames
     const size_t span = (size_t)(j.n - 1) * j.pitch + j.frame_bytes;  // bytes covered in the caller's buffers
     int rc;
     if ((rc = dev_reserve(ctx, L.d_in, span, false))) return rc;
@@ -498,12 +685,9 @@ int lane_submit(nv12eq_ctx* ctx, Lane& L, const Job& j) {
     }
     CK(ctx, cudaMemcpyAsync(d_in, src, span, cudaMemcpyHostToDevice, L.stream));
     ctx->ctr.bytes_in += span;
-    // With UV_SKIP the caller's existing output chroma must survive; with strided frames the padding bytes must
-    // survive too.  In both cases the device output image has to start from the caller's output bytes.
-    const bool preserve_out = !in_place && (j.uv_mode == UV_SKIP || j.stride != j.w || j.pitch != j.frame_bytes) &&
-                              (j.op == Op::Equalize || j.op == Op::Clahe);
-    const bool preserve_bgr = !in_place && (j.op == Op::ColorEq || j.op == Op::ColorClahe) && (j.stride != 3 * j.w);
-    if (preserve_out || preserve_bgr) {
+    // With strided rows the padding bytes of the caller's output must survive: the device image starts from them.
+    const bool preserve_bgr = !in_place && (j.stride != 3 * j.w);
+    if (preserve_bgr) {
         const uint8_t* osrc = j.out;
         if (!is_pinned(j.out)) {
             if ((rc = host_reserve(ctx, L.h_out, span))) return rc;
@@ -513,19 +697,8 @@ int lane_submit(nv12eq_ctx* ctx, Lane& L, const Job& j) {
         CK(ctx, cudaMemcpyAsync(d_out, osrc, span, cudaMemcpyHostToDevice, L.stream));
         ctx->ctr.bytes_in += span;
     }
-    switch (j.op) {
-        case Op::Equalize:
-            rc = launch_equalize(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.uv_mode, L.stream);
-            break;
-        case Op::Clahe:
-            rc = launch_clahe(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.clip, j.tx, j.ty, j.uv_mode, L.stream);
-            break;
-        case Op::ColorEq:
-        case Op::ColorClahe:
-            rc = launch_color(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.color_mode, j.op == Op::ColorClahe,
-                              j.clip, j.tx, j.ty, L.stream);
-            break;
-    }
+    rc = launch_color(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.color_mode, j.op == Op::ColorClahe, j.clip, j.tx,
+                      j.ty, L.stream);
     if (rc) return rc;
     uint8_t* dst = j.out;
     L.user_out = nullptr;
@@ -538,6 +711,7 @@ int lane_submit(nv12eq_ctx* ctx, Lane& L, const Job& j) {
     CK(ctx, cudaMemcpyAsync(L.h_status, ws_status(L.ws), sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream));
     CK(ctx, cudaEventRecord(L.done, L.stream));
     ctx->ctr.bytes_out += span;
+    L.luma_only = false;
     L.out_bytes = span;
     L.frames = j.n;
     L.busy = true;
@@ -547,6 +721,7 @@ int lane_submit(nv12eq_ctx* ctx, Lane& L, const Job& j) {
 int lane_wait(nv12eq_ctx* ctx, Lane& L) {
     if (!L.busy) return NV12EQ_OK;
     L.busy = false;
+    if (ctx->pool) ctx->pool->wait(&L.host_pending);  // chroma tasks read / write the caller's buffers: always drain them
     CK(ctx, cudaEventSynchronize(L.done));
     if (*L.h_status != 0) {
         // a kernel gave up waiting (should be impossible); put the workspace back to a known state
@@ -556,7 +731,10 @@ int lane_wait(nv12eq_ctx* ctx, Lane& L) {
         cudaStreamSynchronize(L.stream);
         return fail(ctx, NV12EQ_ERR_CUDA, "kernel dependency wait timed out");
     }
-    if (L.user_out) memcpy(L.user_out, L.h_out.p, L.out_bytes);
+    if (L.user_out) {
+        if (L.luma_only) copy_luma_host(L.user_out, reinterpret_cast<const uint8_t*>(L.h_out.p), L.frames, L.jpitch, L.jw, L.jh, L.jstride);
+        else memcpy(L.user_out, L.h_out.p, L.out_bytes);
+    }
     L.user_out = nullptr;
     ctx->ctr.frames += (uint64_t)L.frames;
     return NV12EQ_OK;
@@ -691,6 +869,7 @@ void nv12eq_destroy(nv12eq_ctx* ctx) {
     }
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
     ws_release(ctx->dev_ws);
+    delete ctx->pool;
     delete ctx;
 }
 
@@ -934,21 +1113,32 @@ int stream_fail(nv12eq_stream* s, int status, const char* msg) {
     if (s) { s->last_error = msg; if (s->ctx) s->ctx->last_error = msg; }
     return status;
 }
-// Launch one frame on a lane whose pinned input already holds the frame.
+Job stream_job(const nv12eq_stream* s, const Lane& L) {
+    const nv12eq_stream_config& c = s->cfg;
+    return make_nv12_job(c.op == NV12EQ_OP_CLAHE ? Op::Clahe : Op::Equalize, reinterpret_cast<const uint8_t*>(L.h_in.p),
+                         reinterpret_cast<uint8_t*>(L.h_out.p), 1, s->frame_bytes, c.width, c.height, c.stride, c.uv_mode, c.clip_limit,
+                         c.tiles_x, c.tiles_y);
+}
+// Launch one frame on a lane whose pinned input already holds the luma plane: only the luma crosses PCIe.
 int stream_launch(nv12eq_stream* s, Lane& L) {
     nv12eq_ctx* ctx = s->ctx;
-    const nv12eq_stream_config& c = s->cfg;
+    const Job j = stream_job(s, L);
     uint8_t* d_in = reinterpret_cast<uint8_t*>(L.d_in.p);
     uint8_t* d_out = reinterpret_cast<uint8_t*>(L.d_out.p);
-    CK(ctx, cudaMemcpyAsync(d_in, L.h_in.p, s->frame_bytes, cudaMemcpyHostToDevice, L.stream));
-    int rc = (c.op == NV12EQ_OP_CLAHE)
-                 ? launch_clahe(ctx, L.ws, d_in, d_out, 1, s->frame_bytes, c.width, c.height, c.stride, c.clip_limit, c.tiles_x,
-                                c.tiles_y, c.uv_mode, L.stream)
-                 : launch_equalize(ctx, L.ws, d_in, d_out, 1, s->frame_bytes, c.width, c.height, c.stride, c.uv_mode, L.stream);
+    int rc = copy_luma_async(ctx, d_in, j.in, j, cudaMemcpyHostToDevice, L.stream);
     if (rc) return rc;
-    CK(ctx, cudaMemcpyAsync(L.h_out.p, d_out, s->frame_bytes, cudaMemcpyDeviceToHost, L.stream));
+    rc = (j.op == Op::Clahe) ? launch_clahe(ctx, L.ws, d_in, d_out, 1, j.pitch, j.w, j.h, j.stride, j.clip, j.tx, j.ty, UV_SKIP, L.stream)
+                             : launch_equalize(ctx, L.ws, d_in, d_out, 1, j.pitch, j.w, j.h, j.stride, UV_SKIP, L.stream);
+    if (rc) return rc;
+    if ((rc = copy_luma_async(ctx, j.out, d_out, j, cudaMemcpyDeviceToHost, L.stream))) return rc;
     CK(ctx, cudaEventRecord(L.done, L.stream));
     return NV12EQ_OK;
+}
+// rows of `w` payload bytes between two frames of the stream's layout: r0 <= row < r1 (luma rows 0..h, chroma rows h..h+h/2)
+void stream_copy_rows(const nv12eq_stream* s, uint8_t* dst, const uint8_t* src, int r0, int r1) {
+    const size_t stride = (size_t)s->cfg.stride, w = (size_t)s->cfg.width;
+    if (stride == w) memcpy(dst + r0 * stride, src + r0 * stride, (size_t)(r1 - r0) * stride);
+    else for (int r = r0; r < r1; ++r) memcpy(dst + r * stride, src + r * stride, w);
 }
 }  // namespace
 
@@ -977,6 +1167,14 @@ int nv12eq_stream_open(nv12eq_ctx* ctx, const nv12eq_stream_config* cfg, nv12eq_
         if (ok && !rc) rc = dev_reserve(ctx, L.d_out, s->frame_bytes, true);
         if (ok && !rc) rc = host_reserve(ctx, L.h_in, s->frame_bytes);
         if (ok && !rc) rc = host_reserve(ctx, L.h_out, s->frame_bytes);
+        if (ok && !rc) {
+            // the staged output frame: payload bytes the stream never writes start at zero; neutral chroma is written once
+            memset(L.h_out.p, 0, s->frame_bytes);
+            if (cfg->uv_mode == UV_GRAY128) {
+                uint8_t* o = reinterpret_cast<uint8_t*>(L.h_out.p);
+                for (int r = cfg->height; r < cfg->height + cfg->height / 2; ++r) memset(o + (size_t)r * cfg->stride, 128, (size_t)cfg->width);
+            }
+        }
         if (!ok || rc) {
             if (!rc) rc = fail(ctx, NV12EQ_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
             nv12eq_stream_close(s);
@@ -1019,8 +1217,11 @@ int nv12eq_stream_push(nv12eq_stream* s, const uint8_t* in, size_t in_size, uint
     const size_t tail = (s->head + s->count) % depth;
     Lane& L = s->lanes[tail];
     lk.unlock();
-    // the tail lane is free (not in [head, head+count)) and only the producer touches free lanes
-    memcpy(L.h_in.p, in, s->frame_bytes);
+    // the tail lane is free (not in [head, head+count)) and only the producer touches free lanes.  Luma goes to the
+    // pinned upload buffer; passthrough chroma goes straight to the staged output frame and never crosses PCIe.
+    const int H = s->cfg.height;
+    stream_copy_rows(s, reinterpret_cast<uint8_t*>(L.h_in.p), in, 0, H);
+    if (s->cfg.uv_mode == UV_COPY) stream_copy_rows(s, reinterpret_cast<uint8_t*>(L.h_out.p), in, H, H + H / 2);
     const auto now = std::chrono::steady_clock::now();
     int rc = stream_launch(s, L);
     if (rc) return rc;
@@ -1067,7 +1268,10 @@ int nv12eq_stream_pop(nv12eq_stream* s, uint8_t* out, size_t out_size, uint64_t*
         return nv12eq_stream_pop(s, out, out_size, out_seq, block);
     }
     // copy out under the lock: a DROP_OLDEST producer must not recycle the lane while it is being read
-    memcpy(out, L.h_out.p, s->frame_bytes);
+    {
+        const int H = s->cfg.height;
+        stream_copy_rows(s, out, reinterpret_cast<const uint8_t*>(L.h_out.p), 0, s->cfg.uv_mode == UV_SKIP ? H : H + H / 2);
+    }
     const uint64_t us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - s->t_push[h]).count();
     s->head = (s->head + 1) % depth;
     s->count--;
