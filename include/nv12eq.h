@@ -19,6 +19,8 @@
  *                                          accel.cpp:36-61 (device buffers in, device buffers out)
  *   nv12eq_color_equalize / _clahe      <- cvtColor(BGR2YUV) -> split -> equalizeHist/CLAHE(Y) -> merge ->
  *                                          cvtColor(YUV2BGR), singlecolor.cpp:39-66, clahe1frame.cpp:83-102
+ *   nv12eq_bgr_to_i420 / _device        <- cvtColor(bgr, COLOR_BGR2YUV_I420) in front of the Y-plane operator,
+ *                                          1frameMeasure.cpp:32-35
  *   nv12eq_get_counters                 <- the Counters struct + status tick, OpenCLequalHist.cpp:45-61,439-508
  *   nv12eq_stream_*                     <- the frame queue between capture and encoder: GAsyncQueue + worker threads
  *                                          (OpenCVequalHist.cpp:71-98,102-196,397-402) with the leaky queues around them
@@ -170,6 +172,12 @@ int nv12eq_color_equalize_device(nv12eq_ctx* ctx, const uint8_t* d_bgr_in, uint8
 int nv12eq_color_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_bgr_in, uint8_t* d_bgr_out, int n_frames,
                               size_t frame_pitch, int width, int height, int stride, int color_mode, double clip_limit,
                               int tiles_x, int tiles_y, void* cuda_stream);
+
+/* ---- BGR -> I420 adapter (1frameMeasure.cpp:32): packed 8-bit BGR in, planar Y[h][w] U[h/2][w/2] V[h/2][w/2] out ---- */
+/* width and height must be even (OpenCV rejects odd sizes for this conversion).  out holds w*h*3/2 bytes per frame. */
+int nv12eq_bgr_to_i420(nv12eq_ctx* ctx, const uint8_t* bgr, int width, int height, int stride, uint8_t* out, size_t out_size);
+int nv12eq_bgr_to_i420_device(nv12eq_ctx* ctx, const uint8_t* d_bgr, uint8_t* d_out, int n_frames, size_t bgr_pitch,
+                              size_t out_pitch, int width, int height, int stride, void* cuda_stream);
 
 /* ---- ordered, back-pressured frame stream -------------------------------- */
 /* A stream is the reference's worker queue as one object: frames are pushed in capture order, run on `depth` slots

@@ -103,6 +103,8 @@ _SIGNATURES = {
     "nv12eq_color_clahe": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int]),
     "nv12eq_color_equalize_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "nv12eq_color_clahe_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_vp]),
+    "nv12eq_bgr_to_i420": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_sz]),
+    "nv12eq_bgr_to_i420_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_sz, _c_int, _c_int, _c_int, _c_vp]),
     "nv12eq_stream_open": (_c_int, [_c_vp, ctypes.POINTER(StreamConfig), ctypes.POINTER(_c_vp)]),
     "nv12eq_stream_push": (_c_int, [_c_vp, _c_vp, _c_sz, ctypes.POINTER(ctypes.c_uint64)]),
     "nv12eq_stream_pop": (_c_int, [_c_vp, _c_vp, _c_sz, ctypes.POINTER(ctypes.c_uint64), _c_int]),
@@ -383,6 +385,19 @@ class Context:
         self._check(self._lib.nv12eq_color_clahe_device(self._h, _ptr(d_in), _ptr(d_out), n_frames, frame_pitch, width,
                                                         height, stride, color_mode, float(clip_limit), int(tiles[0]),
                                                         int(tiles[1]), _stream_ptr(stream)))
+
+    # -- BGR -> I420 adapter ---------------------------------------------------------------------------
+    def bgr_to_i420(self, bgr: np.ndarray, out=None) -> np.ndarray:
+        """``cv2.cvtColor(bgr, COLOR_BGR2YUV_I420)`` (1frameMeasure.cpp:32): (H, W, 3) uint8 -> (H*3/2, W) planar."""
+        h, w, _ = bgr.shape
+        out = np.empty((h * 3 // 2, w), np.uint8) if out is None else out
+        self._check(self._lib.nv12eq_bgr_to_i420(self._h, _ptr(bgr), w, h, bgr.strides[0], _ptr(out), _nbytes(out)))
+        return out
+
+    def bgr_to_i420_device(self, d_bgr, d_out, n_frames, bgr_pitch, out_pitch, width, height, stride=None, stream=None):
+        stride = 3 * width if stride is None else stride
+        self._check(self._lib.nv12eq_bgr_to_i420_device(self._h, _ptr(d_bgr), _ptr(d_out), n_frames, bgr_pitch, out_pitch, width,
+                                                        height, stride, _stream_ptr(stream)))
 
     # -- synthetic inputs -------------------------------------------------------------------------------
     def synth_nv12_device(self, d_out, n_frames, frame_pitch, width, height, stride=None, seed=2026, first_frame=0,

@@ -120,4 +120,67 @@ __global__ void __launch_bounds__(kColorThreads) bgr_recombine_kernel(const Colo
     }
 }
 
+// ---- cvtColor(COLOR_BGR2YUV_I420), 1frameMeasure.cpp:32 ------------------------------------------
+// Q20 limited-range BT.601; chroma taken from the top-left pixel of every 2x2 block; planar output.  One thread
+// converts a 4x2 pixel block: two 12-byte row pieces in, two luma words and two chroma byte pairs out.
+struct I420Params {
+    const uint8_t* bgr; uint8_t* out;
+    unsigned long long bgr_pitch, out_pitch;   // bytes between frames
+    int w, h, stride;                          // even w, h; stride in bytes of a BGR row
+};
+__device__ __forceinline__ uint32_t i420_luma(int B, int G, int R) { return (uint32_t)((269484 * R + 528482 * G + 102760 * B + (16 << 20) + (1 << 19)) >> 20); }
+__device__ __forceinline__ uint32_t i420_u(int B, int G, int R) { return (uint32_t)((-155188 * R - 305135 * G + 460324 * B + (128 << 20) + (1 << 19)) >> 20); }
+__device__ __forceinline__ uint32_t i420_v(int B, int G, int R) { return (uint32_t)((460324 * R - 385875 * G - 74448 * B + (128 << 20) + (1 << 19)) >> 20); }
+
+__global__ void __launch_bounds__(kColorThreads) bgr_to_i420_kernel(const I420Params p) {
+    const int f = blockIdx.y;
+    const uint8_t* src = p.bgr + (unsigned long long)f * p.bgr_pitch;
+    uint8_t* Y = p.out + (unsigned long long)f * p.out_pitch;
+    uint8_t* U = Y + (size_t)p.w * p.h;
+    uint8_t* V = U + (size_t)(p.w / 2) * (p.h / 2);
+    const int bw = (p.w + 3) / 4, bh = p.h / 2;          // 4x2 blocks (the last block of a row may be 2 wide)
+    const long long nblk = (long long)bw * bh;
+    const bool vec = ((p.w & 3) == 0) && ((p.stride & 3) == 0) && ((((uintptr_t)src | (uintptr_t)Y) & 3) == 0) &&
+                     ((((uintptr_t)U | (uintptr_t)V) & 1) == 0);
+    for (long long b = (long long)blockIdx.x * kColorThreads + threadIdx.x; b < nblk; b += (long long)gridDim.x * kColorThreads) {
+        const int by = (int)(b / bw), bx = (int)(b - (long long)by * bw);
+        const int x = bx * 4, y = by * 2;
+        if (vec) {
+            uint32_t luma[2];
+            uint32_t u01 = 0, v01 = 0;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + (size_t)(y + r) * p.stride + 3 * (size_t)x);
+                const uint32_t a = __ldg(s32), bb = __ldg(s32 + 1), c = __ldg(s32 + 2);
+                const int B0 = a & 255, G0 = (a >> 8) & 255, R0 = (a >> 16) & 255;
+                const int B1 = a >> 24, G1 = bb & 255, R1 = (bb >> 8) & 255;
+                const int B2 = (bb >> 16) & 255, G2 = bb >> 24, R2 = c & 255;
+                const int B3 = (c >> 8) & 255, G3 = (c >> 16) & 255, R3 = c >> 24;
+                luma[r] = i420_luma(B0, G0, R0) | (i420_luma(B1, G1, R1) << 8) | (i420_luma(B2, G2, R2) << 16) | (i420_luma(B3, G3, R3) << 24);
+                if (r == 0) {
+                    u01 = i420_u(B0, G0, R0) | (i420_u(B2, G2, R2) << 8);
+                    v01 = i420_v(B0, G0, R0) | (i420_v(B2, G2, R2) << 8);
+                }
+            }
+            *reinterpret_cast<uint32_t*>(Y + (size_t)y * p.w + x) = luma[0];
+            *reinterpret_cast<uint32_t*>(Y + (size_t)(y + 1) * p.w + x) = luma[1];
+            const size_t k = (size_t)by * (p.w / 2) + x / 2;
+            *reinterpret_cast<uint16_t*>(U + k) = (uint16_t)u01;
+            *reinterpret_cast<uint16_t*>(V + k) = (uint16_t)v01;
+        } else {
+            const int xe = min(x + 4, p.w);
+            for (int r = 0; r < 2; ++r)
+                for (int c = x; c < xe; ++c) {
+                    const uint8_t* px = src + (size_t)(y + r) * p.stride + 3 * (size_t)c;
+                    Y[(size_t)(y + r) * p.w + c] = (uint8_t)i420_luma(px[0], px[1], px[2]);
+                    if (r == 0 && !(c & 1)) {
+                        const size_t k = (size_t)by * (p.w / 2) + c / 2;
+                        U[k] = (uint8_t)i420_u(px[0], px[1], px[2]);
+                        V[k] = (uint8_t)i420_v(px[0], px[1], px[2]);
+                    }
+                }
+        }
+    }
+}
+
 }  // namespace nv12eq

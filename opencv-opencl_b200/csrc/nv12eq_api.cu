@@ -1088,6 +1088,62 @@ int nv12eq_color_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_o
 }
 
 
+// ---- BGR -> I420 adapter --------------------------------------------------------------------------------
+static int launch_i420(nv12eq_ctx* ctx, const uint8_t* d_bgr, uint8_t* d_out, int n, size_t bgr_pitch, size_t out_pitch, int w, int h,
+                       int stride, cudaStream_t st) {
+    if (n == 0) return NV12EQ_OK;
+    if (n > 65535) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "at most 65535 frames per call");
+    I420Params p{};
+    p.bgr = d_bgr; p.out = d_out; p.bgr_pitch = bgr_pitch; p.out_pitch = out_pitch; p.w = w; p.h = h; p.stride = stride;
+    const long long blocks = (long long)((w + 3) / 4) * (h / 2);
+    const int gx = (int)std::max<long long>(1, std::min<long long>((blocks + kColorThreads - 1) / kColorThreads, (long long)ctx->sm_count * 8));
+    bgr_to_i420_kernel<<<dim3(gx, n), kColorThreads, 0, st>>>(p);
+    ctx->ctr.kernel_launches++;
+    CK(ctx, cudaGetLastError());
+    return NV12EQ_OK;
+}
+static int check_i420(nv12eq_ctx* ctx, int w, int h, int stride) {
+    int rc = check_color(ctx, w, h, stride, NV12EQ_COLOR_YUV);
+    if (rc) return rc;
+    if ((w & 1) || (h & 1)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "BGR->I420 needs even width and height, got %dx%d", w, h);
+    return NV12EQ_OK;
+}
+
+int nv12eq_bgr_to_i420_device(nv12eq_ctx* ctx, const uint8_t* d_bgr, uint8_t* d_out, int n_frames, size_t bgr_pitch, size_t out_pitch,
+                              int width, int height, int stride, void* cuda_stream) {
+    int rc = check_i420(ctx, width, height, stride);
+    if (rc) return rc;
+    const size_t out_frame = (size_t)width * height * 3 / 2;
+    if (!d_bgr || !d_out || n_frames < 0 || (n_frames > 1 && (bgr_pitch < (size_t)stride * height || out_pitch < out_frame)))
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    DeviceGuard guard(ctx->device);
+    rc = launch_i420(ctx, d_bgr, d_out, n_frames, bgr_pitch, out_pitch, width, height, stride, pick_stream(ctx, cuda_stream));
+    if (!rc) ctx->ctr.frames += (uint64_t)n_frames;
+    return rc;
+}
+
+int nv12eq_bgr_to_i420(nv12eq_ctx* ctx, const uint8_t* bgr, int width, int height, int stride, uint8_t* out, size_t out_size) {
+    int rc = check_i420(ctx, width, height, stride);
+    if (rc) return rc;
+    if (!bgr || !out) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "null frame pointer");
+    const size_t out_frame = (size_t)width * height * 3 / 2;
+    if (out_size < out_frame) return fail(ctx, NV12EQ_ERR_SHORT_BUFFER, "output %zu bytes < I420 frame %zu bytes", out_size, out_frame);
+    DeviceGuard guard(ctx->device);
+    Lane& L = ctx->lanes[0];
+    if ((rc = lane_wait(ctx, L))) return rc;
+    const size_t in_span = (size_t)stride * (height - 1) + 3 * (size_t)width;
+    if ((rc = dev_reserve(ctx, L.d_in, in_span, false))) return rc;
+    if ((rc = dev_reserve(ctx, L.d_out, out_frame, false))) return rc;
+    CK(ctx, cudaMemcpyAsync(L.d_in.p, bgr, in_span, cudaMemcpyHostToDevice, L.stream));
+    rc = launch_i420(ctx, reinterpret_cast<const uint8_t*>(L.d_in.p), reinterpret_cast<uint8_t*>(L.d_out.p), 1, in_span, out_frame, width,
+                     height, stride, L.stream);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(out, L.d_out.p, out_frame, cudaMemcpyDeviceToHost, L.stream));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    ctx->ctr.bytes_in += in_span; ctx->ctr.bytes_out += out_frame; ctx->ctr.frames++;
+    return NV12EQ_OK;
+}
+
 // ---- ordered, back-pressured frame stream ---------------------------------------------------------------
 // FIFO ring of `depth` lanes.  push() takes the tail lane, pop() the head lane, so delivery order == push order by
 // construction; sequence numbers make drops visible to the consumer.

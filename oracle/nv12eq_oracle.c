@@ -379,6 +379,29 @@ ORACLE_API int oracle_color_equalize(const uint8_t* bgr_in, uint8_t* bgr_out, in
     return rc;
 }
 
+/* cv::cvtColor(bgr, COLOR_BGR2YUV_I420) as used by 1frameMeasure.cpp:32: Q20 limited-range BT.601,
+ * chroma sampled at the top-left pixel of every 2x2 block, planar output Y[H][W], U[H/2][W/2], V[H/2][W/2].
+ * W and H must be even (OpenCV rejects odd sizes).  Returns 0, or -1 on bad arguments. */
+ORACLE_API int oracle_bgr2i420(const uint8_t* bgr, int stride, uint8_t* out, int W, int H) {
+    if (!bgr || !out || W <= 0 || H <= 0 || (W & 1) || (H & 1) || stride < 3 * W) return -1;
+    uint8_t* Y = out;
+    uint8_t* U = out + (size_t)W * H;
+    uint8_t* V = U + (size_t)(W / 2) * (H / 2);
+    for (int r = 0; r < H; ++r) {
+        const uint8_t* s = bgr + (size_t)r * stride;
+        for (int c = 0; c < W; ++c) {
+            const int B = s[3 * c], G = s[3 * c + 1], R = s[3 * c + 2];
+            Y[(size_t)r * W + c] = (uint8_t)((269484 * R + 528482 * G + 102760 * B + (16 << 20) + (1 << 19)) >> 20);
+            if (!(r & 1) && !(c & 1)) {
+                const size_t k = (size_t)(r / 2) * (W / 2) + c / 2;
+                U[k] = (uint8_t)((-155188 * R - 305135 * G + 460324 * B + (128 << 20) + (1 << 19)) >> 20);
+                V[k] = (uint8_t)((460324 * R - 385875 * G - 74448 * B + (128 << 20) + (1 << 19)) >> 20);
+            }
+        }
+    }
+    return 0;
+}
+
 /* Colour-path synthetic input (Appendix B): B,G,R planes = Y syntheses with seeds 3026/4026/5026. */
 ORACLE_API void oracle_synth_bgr(uint8_t* bgr, int stride, int W, int H, uint32_t frame) {
     uint8_t* plane = (uint8_t*)malloc((size_t)W * H);

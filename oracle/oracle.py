@@ -83,6 +83,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_bgr2ycc.restype = None
         L.oracle_ycc2bgr.argtypes = [_u8p, c_int, _u8p, c_int, c_int, c_int, c_int]
         L.oracle_ycc2bgr.restype = None
+        L.oracle_bgr2i420.argtypes = [_u8p, c_int, _u8p, c_int, c_int]
+        L.oracle_bgr2i420.restype = c_int
         L.oracle_color_equalize.argtypes = [_u8p, _u8p, c_int, c_int, c_int, c_int, c_int, c_dbl, c_int, c_int]
         L.oracle_color_equalize.restype = c_int
         _lib = L
@@ -207,6 +209,17 @@ def c_color_equalize(bgr: np.ndarray, mode=COLOR_YUV, use_clahe=False, clip=2.0,
     rc = lib().oracle_color_equalize(_p(bgr), _p(out), W, H, 3 * W, mode, int(use_clahe), float(clip), tx, ty)
     if rc:
         raise RuntimeError(f"oracle_color_equalize rc={rc}")
+    return out
+
+
+def c_bgr2i420(bgr: np.ndarray) -> np.ndarray:
+    """COLOR_BGR2YUV_I420 (1frameMeasure.cpp:32): returns the (H*3/2, W) planar image exactly as cv2 lays it out."""
+    bgr = np.ascontiguousarray(bgr)
+    H, W, _ = bgr.shape
+    out = np.empty((H * 3 // 2, W), dtype=np.uint8)
+    rc = lib().oracle_bgr2i420(_p(bgr), 3 * W, _p(out), W, H)
+    if rc:
+        raise ValueError("oracle_bgr2i420: width and height must be even")
     return out
 
 
