@@ -7,6 +7,7 @@
 // input and combines them with the equalized Y.
 #pragma once
 #include "common.cuh"
+#include "equalize.cuh"
 
 namespace nv12eq {
 
@@ -118,6 +119,260 @@ __global__ void __launch_bounds__(kColorThreads) bgr_recombine_kernel(const Colo
             o8[0] = (uint8_t)o; o8[1] = (uint8_t)(o >> 8); o8[2] = (uint8_t)(o >> 16);
         }
     }
+}
+
+
+// ---- fused colour equalization (flat, 16-byte aligned BGR frames) ---------------------------------------------------
+// Two passes over the BGR frame and nothing else: the luma plane is never written.
+//   hist item : BGR chunk -> Y (Q14, two IDP.2A per pixel) -> shared histogram -> global histogram of the frame
+//   apply item: BGR chunk -> Y -> LUT[Y]; chroma re-derived from B, R and Y (saturated to 8 bits exactly as the
+//               intermediate 8UC3 image would hold it) -> inverse conversion with the new luma -> BGR chunk
+// Same ticket-lag schedule and the same histogram-as-completion-flag as equalize_kernel.  Algorithmic bytes per frame:
+// 6*W*H (read BGR, write BGR); this kernel moves 9*W*H (BGR is read twice) against 14*W*H of the three-pass form.
+// A warp owns 512 consecutive pixels (1536 bytes) per round: every lane cp.asyncs three 16-byte pieces (coalesced),
+// then reads back its own 48 bytes = 16 pixels (conflict-free 16-byte LDS at a 48-byte stride).
+struct ColorEqParams {
+    const uint8_t* in;
+    uint8_t* out;
+    unsigned long long pitch;   // bytes between BGR frames
+    int n_frames;
+    unsigned long long rounds;  // warp rounds per frame = ceil(W*H / 512)
+    unsigned long long npx;     // W*H (multiple of 16)
+    int chunks;                 // C items per frame and phase
+    unsigned long long rounds_chunk;
+    int lag;
+    int kB, kR;                 // forward chroma gains: c1 = descale((B - Y) * kB), c2 = descale((R - Y) * kR)
+    int iB, iG1, iG2, iR;       // inverse: B = Y + descale(c1*iB), G = Y + descale(c1*iG1 + c2*iG2), R = Y + descale(c2*iR)
+    uint32_t* hist;     // [n_frames][256], zero on entry, self-cleaned
+    uint32_t* applied;  // [n_frames]
+    uint32_t* ticket;
+    uint32_t* status;
+};
+constexpr int kColorRingDepth = 3;                       // warp rounds in flight
+constexpr int kColorRoundBytes = 1536;                   // 512 pixels
+constexpr int kColorRingBytes = kWarps * kColorRingDepth * kColorRoundBytes;
+constexpr int kColorEqSmemBytes = kLaneTableBytes + kColorRingBytes;
+
+// pixel i (0..3) of a 12-byte group {q0, q1, q2} as an aligned word {B, G, R, x}
+template <int I>
+__device__ __forceinline__ uint32_t bgr_px(uint32_t q0, uint32_t q1, uint32_t q2) {
+    if (I == 0) return q0;
+    if (I == 1) return __byte_perm(q0, q1, 0x6543);
+    if (I == 2) return __byte_perm(q1, q2, 0x5432);
+    return q2 >> 8;
+}
+// IDP.2A: a = two 16-bit factors, b = four bytes; lo uses bytes 0,1 of b, hi bytes 2,3.  The pixel bytes are unsigned;
+// the chroma gains come as {+k, -k} signed halves.
+__device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp2a_lo(a, b, c); }
+__device__ __forceinline__ uint32_t dp2a_hi_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp2a_hi(a, b, c); }
+__device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_lo_us(uint32_t a, uint32_t b, int c) {  // unsigned 16-bit factors x signed bytes
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_lo_ss(int a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// I2IP: d = (c << 16) | (sat(a) << 8) | sat(b) -- two saturating conversions and a pack in one instruction
+__device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_sat_s8(int a, int b, uint32_t c) {
+    uint32_t d;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// keeps a value opaque so that (x >> 14) << 7 is not re-associated into shift + mask + add (SHF + LEA is one less)
+__device__ __forceinline__ uint32_t opaque(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+// Q14 luma before the shift: 1868*B + 9617*G + 4899*R + 8192 (two IDP.2A); byte 3 of px (the next pixel's B, or 0) is
+// multiplied by the zero high half of the second factor word
+__device__ __forceinline__ uint32_t bgr_luma14(uint32_t px) {
+    return dp2a_hi_uu(4899u, px, dp2a_lo_uu((9617u << 16) | 1868u, px, 8192u));
+}
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kThreads, MIN_CTAS) color_equalize_kernel(const ColorEqParams p) {
+    extern __shared__ __align__(16) uint32_t smem[];  // 32 KB lane table (hist or LUT), then the per-warp cp.async rings
+    __shared__ __align__(16) uint8_t s_lut[256];
+    __shared__ uint32_t s_ticket[2];
+    __shared__ int s_flag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lane_base = smem_u32(smem) + lane * 4;
+    const uint32_t ring = smem_u32(smem) + kLaneTableBytes + (uint32_t)warp * (kColorRingDepth * kColorRoundBytes);
+    const int C = p.chunks;
+    const int lag = p.lag;
+    const uint32_t total_items = (uint32_t)(p.n_frames + lag) * (uint32_t)(2 * C);
+    const unsigned long long total_vec = p.npx * 3 / 16;  // 16-byte pieces in a frame
+
+    TicketQueue q{p.ticket, s_ticket, 0u, 0u, false};
+    q.start();
+    for (;;) {
+        const uint32_t item = q.current();
+        if (item >= total_items) break;
+        const int g = (int)(item / (uint32_t)(2 * C));
+        const int r2c = (int)(item % (uint32_t)(2 * C));
+        const bool hist_item = r2c < C;
+        const int c = hist_item ? r2c : r2c - C;
+        const int f = g - lag;
+        const unsigned long long rd0 = min((unsigned long long)c * p.rounds_chunk, p.rounds);
+        const unsigned long long rd1 = min(rd0 + p.rounds_chunk, p.rounds);
+        // rounds of this warp: rd0 + warp, rd0 + warp + kWarps, ...
+        const long long nr = rd1 > rd0 + warp ? (long long)((rd1 - rd0 - warp + kWarps - 1) / kWarps) : 0;
+
+        // issue the three 16-byte pieces of this lane for warp round `k` (0-based within the item) into ring stage k % depth
+        auto issue = [&](const uint8_t* frame, long long k) {
+            if (k < nr) {
+                const unsigned long long round = rd0 + warp + (unsigned long long)k * kWarps;
+                const unsigned long long v0 = round * 96;  // first 16-byte piece of the round
+                const uint32_t st = ring + (uint32_t)(k % kColorRingDepth) * kColorRoundBytes;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const unsigned long long v = v0 + lane + 32 * j;
+                    if (v < total_vec) cp_async16(st + (uint32_t)(lane + 32 * j) * 16u, frame + v * 16);
+                }
+            }
+            cp_async_commit();
+        };
+
+        if (hist_item && g < p.n_frames) {
+            // ---------------- histogram of chunk c of frame g ----------------
+            const uint8_t* frame = p.in + (unsigned long long)g * p.pitch;
+            lane_table_zero(smem);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kColorRingDepth - 1; ++k) issue(frame, k);
+            for (long long k = 0; k < nr; ++k) {
+                if (k + 2 >= nr) q.prefetch();  // late: an early draw would queue the next item behind this one
+                issue(frame, k + kColorRingDepth - 1);
+                cp_async_wait<kColorRingDepth - 1>();
+                __syncwarp();
+                const unsigned long long px0 = (rd0 + warp + (unsigned long long)k * kWarps) * 512 + (unsigned long long)lane * 16;
+                if (px0 < p.npx) {
+                    const uint32_t st = ring + (uint32_t)(k % kColorRingDepth) * kColorRoundBytes + (uint32_t)lane * 48u;
+                    const int4 a = lds_s4(st), b = lds_s4(st + 16), cc = lds_s4(st + 32);
+                    const uint32_t qw[12] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y,
+                                             (uint32_t)b.z, (uint32_t)b.w, (uint32_t)cc.x, (uint32_t)cc.y, (uint32_t)cc.z, (uint32_t)cc.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint32_t q0 = qw[3 * t], q1 = qw[3 * t + 1], q2 = qw[3 * t + 2];
+                        red_shared_inc(lane_base + (opaque(bgr_luma14(bgr_px<0>(q0, q1, q2)) >> 14) << 7));
+                        red_shared_inc(lane_base + (opaque(bgr_luma14(bgr_px<1>(q0, q1, q2)) >> 14) << 7));
+                        red_shared_inc(lane_base + (opaque(bgr_luma14(bgr_px<2>(q0, q1, q2)) >> 14) << 7));
+                        red_shared_inc(lane_base + (opaque(bgr_luma14(bgr_px<3>(q0, q1, q2)) >> 14) << 7));
+                    }
+                }
+                __syncwarp();  // the stage is re-filled two rounds from now by this warp's own cp.asyncs
+            }
+            __syncthreads();
+            if (tid < 256) {
+                const uint32_t cnt = lane_table_row_sum(smem, tid);
+                if (cnt) atomicAdd(p.hist + (size_t)g * 256 + tid, cnt);
+            }
+        } else if (!hist_item && f >= 0) {
+            // ---------------- LUT + recombine for chunk c of frame f ----------------
+            const uint8_t* frame = p.in + (unsigned long long)f * p.pitch;
+            uint8_t* dst = p.out + (unsigned long long)f * p.pitch;
+#pragma unroll
+            for (int k = 0; k < kColorRingDepth - 1; ++k) issue(frame, k);  // pixels stream in while the LUT is built
+            if (warp == 0) {
+                uint32_t* gh = p.hist + (size_t)f * 256;
+                bool ok = equalize_lut_warp(gh, (long long)p.npx, (long long)p.npx, s_lut, lane);
+                if (!ok) {
+                    const long long t0 = clock64();
+                    unsigned ns = 64;
+                    while (!(ok = equalize_lut_warp(gh, (long long)p.npx, (long long)p.npx, s_lut, lane))) {
+                        __nanosleep(ns);
+                        if (ns < 2048) ns <<= 1;
+                        if (clock64() - t0 > kSpinCycles) break;
+                    }
+                }
+                if (lane == 0) {
+                    s_flag = ok;
+                    if (!ok) atomicExch(p.status, 1u);
+                }
+                if (ok) {
+                    uint32_t last = 0;
+                    if (lane == 0) last = (atomicAdd(p.applied + f, 1u) == (uint32_t)(C - 1));
+                    if (__shfl_sync(0xffffffffu, last, 0)) {
+                        uint4* g4 = reinterpret_cast<uint4*>(gh) + lane * 2;
+                        g4[0] = make_uint4(0, 0, 0, 0);
+                        g4[1] = make_uint4(0, 0, 0, 0);
+                        if (lane == 0) p.applied[f] = 0;
+                    }
+                }
+            }
+            __syncthreads();
+            if (!s_flag) break;
+            lane_table_fill_from_lut(smem, s_lut);
+            __syncthreads();
+            const int kBn = -p.kB, kRn = -p.kR;
+            const int cB = (int)(((uint32_t)(kBn & 0xffff) << 16) | (uint32_t)(p.kB & 0xffff));  // {kB, -kB} as s16x2
+            const int cR = (int)(((uint32_t)(kRn & 0xffff) << 16) | (uint32_t)(p.kR & 0xffff));
+            const uint32_t fB = (uint32_t)p.iB & 0xffffu;                                   // {iB, 0}: multiplies c1 only
+            const uint32_t fR = ((uint32_t)p.iR & 0xffffu) << 16;                           // {0, iR}: multiplies c2 only
+            const int fG = (int)((((uint32_t)p.iG2 & 0xffffu) << 16) | ((uint32_t)p.iG1 & 0xffffu));
+            for (long long k = 0; k < nr; ++k) {
+                if (k + 2 >= nr) q.prefetch();
+                issue(frame, k + kColorRingDepth - 1);
+                cp_async_wait<kColorRingDepth - 1>();
+                __syncwarp();
+                const unsigned long long round = rd0 + warp + (unsigned long long)k * kWarps;
+                const unsigned long long px0 = round * 512 + (unsigned long long)lane * 16;
+                if (px0 < p.npx) {
+                    const uint32_t st = ring + (uint32_t)(k % kColorRingDepth) * kColorRoundBytes + (uint32_t)lane * 48u;
+                    const int4 a = lds_s4(st), b = lds_s4(st + 16), cc = lds_s4(st + 32);
+                    const uint32_t qw[12] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y,
+                                             (uint32_t)b.z, (uint32_t)b.w, (uint32_t)cc.x, (uint32_t)cc.y, (uint32_t)cc.z, (uint32_t)cc.w};
+                    uint32_t ow[12];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint32_t q0 = qw[3 * t], q1 = qw[3 * t + 1], q2 = qw[3 * t + 2];
+                        uint32_t o[4];
+                        const uint32_t px[4] = {bgr_px<0>(q0, q1, q2), bgr_px<1>(q0, q1, q2), bgr_px<2>(q0, q1, q2), bgr_px<3>(q0, q1, q2)};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t Y = opaque(bgr_luma14(px[i]) >> 14);
+                            const int y2 = (int)lds_u8(lane_base + (Y << 7));
+                            const uint32_t byry = __byte_perm(px[i], Y, 0x4240);            // {B, Y, R, Y}
+                            const int c1 = dp2a_lo_su(cB, byry, 8192) >> 14;                 // descale((B - Y) * kB): never saturates
+                            const int c2 = dp2a_hi_su(cR, byry, 8192) >> 14;                 // descale((R - Y) * kR)
+                            // {c1, sat8s(c2)} as signed bytes: sat8(128 + c2) - 128 is the chroma the 8UC3 image would hold
+                            const uint32_t cc8 = pack_sat_s8(c2, c1, 0u);
+                            const int b2 = y2 + (dp2a_lo_us(fB, cc8, 8192) >> 14);           // Y + descale(c1*iB)
+                            const int g2 = y2 + (dp2a_lo_ss(fG, cc8, 8192) >> 14);           // Y + descale(c1*iG1 + c2*iG2)
+                            const int r2v = y2 + (dp2a_lo_us(fR, cc8, 8192) >> 14);          // Y + descale(c2*iR)
+                            o[i] = pack_sat_u8(g2, b2, pack_sat_u8(0, r2v, 0u));             // {B, G, R, 0}, each saturated
+                        }
+                        ow[3 * t] = __byte_perm(o[0], o[1], 0x4210);       // B0 G0 R0 B1
+                        ow[3 * t + 1] = __byte_perm(o[1], o[2], 0x5421);   // G1 R1 B2 G2
+                        ow[3 * t + 2] = __byte_perm(o[2], o[3], 0x6542);   // R2 B3 G3 R3
+                    }
+                    uint4* d4 = reinterpret_cast<uint4*>(dst + px0 * 3);
+                    __stcs(d4, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+                    __stcs(d4 + 1, make_uint4(ow[4], ow[5], ow[6], ow[7]));
+                    __stcs(d4 + 2, make_uint4(ow[8], ow[9], ow[10], ow[11]));
+                }
+                __syncwarp();
+            }
+        }
+        q.advance();
+    }
+    q.finish();
 }
 
 // ---- cvtColor(COLOR_BGR2YUV_I420), 1frameMeasure.cpp:32 ------------------------------------------

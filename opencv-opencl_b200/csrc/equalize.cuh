@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
     for (;;) {
         const uint32_t item = q.current();
         if (item >= total_items) break;
+#ifdef NV12EQ_EQ_EARLY_TICKET
         q.prefetch();
+#endif
         const int g = (int)(item / (uint32_t)(2 * C));
         const int r2 = (int)(item % (uint32_t)(2 * C));
         const bool hist_item = r2 < C;
@@ -177,7 +179,11 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
             __syncthreads();
             const PlaneChunk pc = plane_chunk(p.flat, c, p.y_bytes, p.y_chunk, p.h, p.y_rows_chunk);
             if (p.flat) {
-                hist_span(y + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, lane_base);
+                // the next ticket is drawn when ~3/4 of the item is done (see TicketQueue): the last quarter hides the atomic
+                const size_t n = (size_t)(pc.b1 - pc.b0), n1 = (n - n / 4) & ~(size_t)4095;
+                hist_span(y + pc.b0, n1, tid, kThreads, lane_base);
+                q.prefetch();
+                hist_span(y + pc.b0 + n1, n - n1, tid, kThreads, lane_base);
             } else {
                 for (int r = pc.r0 + warp; r < pc.r1; r += kWarps)
                     hist_span(y + (size_t)r * p.stride, (size_t)p.w, lane, 32, lane_base);
@@ -229,7 +235,10 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) equalize_kernel(const EqPa
             __syncthreads();
             const PlaneChunk pc = plane_chunk(p.flat, c, p.y_bytes, p.y_chunk, p.h, p.y_rows_chunk);
             if (p.flat) {
-                lut_span(src + pc.b0, dst + pc.b0, (size_t)(pc.b1 - pc.b0), tid, kThreads, lane_base);
+                const size_t n = (size_t)(pc.b1 - pc.b0), n1 = (n - n / 4) & ~(size_t)4095;
+                lut_span(src + pc.b0, dst + pc.b0, n1, tid, kThreads, lane_base);
+                q.prefetch();
+                lut_span(src + pc.b0 + n1, dst + pc.b0 + n1, n - n1, tid, kThreads, lane_base);
             } else {
                 for (int r = pc.r0 + warp; r < pc.r1; r += kWarps)
                     lut_span(src + (size_t)r * p.stride, dst + (size_t)r * p.stride, (size_t)p.w, lane, 32, lane_base);

@@ -275,6 +275,7 @@ int ensure_attrs(nv12eq_ctx* ctx) {
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
+    CK(ctx, cudaFuncSetAttribute(color_equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kColorEqSmemBytes));
     CK(ctx, cudaFuncSetAttribute(clahe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
     CK(ctx, cudaFuncSetAttribute(clahe_kernel<kClaheCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
     ctx->attrs_set = true;
@@ -332,14 +333,14 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
     p.uv_chunk = std::max<unsigned long long>(4096, round4k((p.uv_bytes + C - 1) / C));
     p.y_rows_chunk = (int)((h + C - 1) / C);
     p.uv_rows_chunk = (int)((h / 2 + C - 1) / C);
-    // Frame lag between a frame's histogram items and its apply items.  An item drawn with ticket t finishes when
-    // the counter is near t + grid (every resident CTA finishes about one item per item time), so the histogram
-    // items of a frame are done once grid more tickets have been drawn: lag >= grid / items_per_slot (+1 margin).
-    // The Y planes of `lag` frames have to stay in L2 for the second read: cap the footprint at ~64 MB.
+    // Frame lag between a frame's histogram items and its apply items.  All resident CTAs finish about one item per
+    // item time, so the histogram items of a frame are done once ~grid more tickets have been drawn: lag ~ grid /
+    // items_per_slot.  Measured on B200 with tickets drawn late (tools/sweep.py): best lag 2 at 4K (296 CTAs / 128 items),
+    // 8 at 1080p (296 / 32) -- i.e. floor(grid / items_per_slot).  The Y planes of `lag` frames have to stay in L2 for
+    // the second read: cap the footprint at ~48 MB.
     {
         const long long grid_ctas = (long long)ctx->sm_count * per_sm;
-        // measured on B200 (tools/sweep.py): the best lag is ceil(grid / items_per_slot + 0.6)
-        long long lag = (10 * grid_ctas + 6 * 2 * C + 10 * 2 * C - 1) / (10 * 2 * C);
+        long long lag = std::max<long long>(1, grid_ctas / (2 * C));
         const long long cap = std::max<long long>(1, (48ll << 20) / (long long)std::max<unsigned long long>(1, p.y_bytes));
         lag = std::min(lag, cap);
         if (ctx->tune_lag > 0) lag = ctx->tune_lag;
@@ -527,9 +528,47 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
 // ---------------------------------------------------------------------------------------------------------
 // colour path
 // ---------------------------------------------------------------------------------------------------------
+// Fused two-pass colour equalization (color.cuh::color_equalize_kernel) for flat, 16-byte aligned frames.
+int launch_color_fused(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d_out, int n, size_t pitch, int w, int h, int mode,
+                       cudaStream_t st) {
+    int rc = ensure_attrs(ctx);
+    if (rc) return rc;
+    rc = ws_reserve_frames(ctx, ws, n);
+    if (rc) return rc;
+    ColorEqParams p{};
+    p.in = d_in; p.out = d_out; p.pitch = pitch; p.n_frames = n;
+    p.npx = (unsigned long long)w * h;
+    p.rounds = (p.npx + 511) / 512;
+    const int ctas = ctx->sm_count * 2;
+    long long C = (long long)((p.rounds + 255) / 256);  // ~128K pixels (384 KB of BGR) per item
+    if ((long long)n * C < 2ll * ctas) C = std::min<long long>((2ll * ctas + n - 1) / n, (long long)((p.rounds + 15) / 16));
+    C = std::max<long long>(1, std::min<long long>(C, 1 << 16));
+    p.chunks = (int)C;
+    p.rounds_chunk = (p.rounds + C - 1) / C;
+    long long lag = (10ll * ctas + 16 * 2 * C - 1) / (10 * 2 * C);
+    lag = std::min<long long>(lag, 8);
+    if (ctx->tune_lag > 0) lag = ctx->tune_lag;
+    p.lag = (int)std::min<long long>(lag, std::max(n - 1, 0));
+    if (mode == COLOR_YUV) { p.kB = 8061; p.kR = 14369; p.iB = 33292; p.iG1 = -6472; p.iG2 = -9519; p.iR = 18678; }
+    else { p.kB = 9241; p.kR = 11682; p.iB = 29049; p.iG1 = -5636; p.iG2 = -11698; p.iR = 22987; }
+    p.hist = reinterpret_cast<uint32_t*>(ws.hist.p);
+    p.applied = ws_counter(ws, 1);
+    p.ticket = ws_ticket(ws);
+    p.status = ws_status(ws);
+    const long long items = (long long)(n + p.lag) * 2 * C;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ctas, items));
+    color_equalize_kernel<2><<<grid, kThreads, kColorEqSmemBytes, st>>>(p);
+    ctx->ctr.kernel_launches++;
+    CK(ctx, cudaGetLastError());
+    return NV12EQ_OK;
+}
+
 int launch_color(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d_out, int n, size_t pitch, int w, int h,
                  int stride, int mode, bool use_clahe, double clip, int tx, int ty, cudaStream_t st) {
     if (n == 0) return NV12EQ_OK;
+    const bool fused_ok = !use_clahe && stride == 3 * w && ((long long)w * h) % 16 == 0 && (pitch % 16 == 0 || n == 1) &&
+                          ((((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0) && !getenv("NV12EQ_COLOR_THREE_PASS");
+    if (fused_ok) return launch_color_fused(ctx, ws, d_in, d_out, n, pitch, w, h, mode, st);
     const size_t plane = (size_t)w * h;
     int rc = dev_reserve(ctx, ws.luma, 2 * plane * n + 64, false);
     if (rc) return rc;

@@ -347,3 +347,20 @@ def test_color_device_batch_and_stride(nv, ctx, oracle, torch):
     ctx.color_equalize(wide[:, :W], nv.COLOR_YCRCB, out=out[:, :W])
     assert np.array_equal(out[:, :W], oracle.c_color_equalize(frames[0], oracle.COLOR_YCRCB))
     assert (out[:, W:] == 5).all()
+
+
+def test_color_full_bgr_cube(nv, oracle):
+    """All 2^24 BGR values (a 4096x4096 image) through the fused two-pass colour equalization, both conversions: every
+    saturation corner of the Q14 forward / inverse formulas is hit.  Also a size whose pixel count is not a multiple of
+    512 (ragged last warp round) and an in-place call."""
+    cube = np.arange(1 << 24, dtype=np.uint32)
+    bgr = np.stack([(cube & 255), (cube >> 8) & 255, (cube >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
+    with nv.Context(0, 4096, 4096, 1) as c:
+        for mode, omode in ((nv.COLOR_YUV, oracle.COLOR_YUV), (nv.COLOR_YCRCB, oracle.COLOR_YCRCB)):
+            assert np.array_equal(c.color_equalize(bgr, mode), oracle.c_color_equalize(bgr, omode)), mode
+        small = oracle.c_synth_bgr(328, 202, 3)            # 66256 pixels = 129 rounds + 208 pixels
+        want = oracle.c_color_equalize(small, oracle.COLOR_YUV)
+        assert np.array_equal(c.color_equalize(small, nv.COLOR_YUV), want)
+        buf = small.copy()
+        c.color_equalize(buf, nv.COLOR_YUV, out=buf)
+        assert np.array_equal(buf, want)
