@@ -8,7 +8,8 @@ path = "/tmp/nv12eq_trace.bin"
 os.environ["NV12EQ_TRACE"] = path
 import torch
 import opencv_opencl_b200 as nv12eq
-W, H, n = 3840, 2160, int(sys.argv[1]) if len(sys.argv) > 1 else 64
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+W, H = {"4k": (3840, 2160), "1080p": (1920, 1080), "720p": (1280, 720)}[sys.argv[3] if len(sys.argv) > 3 else "4k"]
 lag = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 pitch = nv12eq.nv12_frame_bytes(W, H)
 ctx = nv12eq.Context(0, W, H, 1)
