@@ -293,11 +293,6 @@ int check_geometry(nv12eq_ctx* ctx, int w, int h, int stride, int n, size_t pitc
     return NV12EQ_OK;
 }
 
-int grid_for(nv12eq_ctx* ctx, long long items, int default_ctas) {
-    int per_sm = ctx->tune_ctas > 0 ? ctx->tune_ctas : default_ctas;
-    long long g = (long long)ctx->sm_count * per_sm;
-    return (int)std::max<long long>(1, std::min<long long>(g, items));
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // equalizeHist launch planning

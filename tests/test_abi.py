@@ -107,3 +107,18 @@ def test_missing_library_is_an_import_error(nv, tmp_path, monkeypatch):
     monkeypatch.setattr(pkg, "_lib", None)
     with pytest.raises(ImportError):
         pkg.load_library()
+
+
+def test_cpp_example_builds_and_fails_loudly_without_a_gpu(nv):
+    """examples/worker_demo.cpp is the reference's worker loop with the OpenCV calls replaced by the C-ABI, in C++.  It
+    must compile against include/nv12eq.h + libnv12eq.so with plain g++; without a GPU it reports the error and exits 1
+    (frames are counted as errors and dropped, like the reference's processing_errors)."""
+    ex = os.path.join(ROOT, "examples")
+    subprocess.run(["make", "-C", ex, "-B", "-s"], check=True)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the run is covered by tests/test_gpu_stream.py")
+    out = subprocess.run([os.path.join(ex, "worker_demo"), "--frames", "3", "--width", "64", "--height", "32"],
+                         capture_output=True, text=True)
+    assert out.returncode == 1
+    assert "no CPU fallback" in out.stderr and "errors" in out.stdout

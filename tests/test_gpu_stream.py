@@ -154,3 +154,17 @@ def test_spatial_split_equalizer_single_rank(nv, ctx, oracle):
     torch.cuda.synchronize()
     assert np.array_equal(hist.cpu().numpy(), oracle.c_hist256(y.reshape(H, W)))
     assert np.array_equal(d_out.cpu().numpy().reshape(H, W), oracle.c_equalize_hist(y.reshape(H, W)))
+
+
+def test_cpp_example_runs_both_modes(nv):
+    """The C++ example (reference worker loop over the C-ABI): worker pool + reorder buffer, and the nv12eq_stream form."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ex = os.path.join(root, "examples")
+    subprocess.run(["make", "-C", ex, "-B", "-s"], check=True)
+    for extra in (["--workers", "3"], ["--stream"], ["--op", "clahe", "--stream"], ["--op", "clahe", "--workers", "2"]):
+        out = subprocess.run([os.path.join(ex, "worker_demo"), "--frames", "24", "--width", "640", "--height", "360"] + extra,
+                             capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "processed 24, delivered in order 24, out of order 0, errors 0" in out.stdout, out.stdout
