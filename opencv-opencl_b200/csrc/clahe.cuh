@@ -426,34 +426,34 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                         // kRingDepth-1 ahead are in flight (about 60 KB per SM) without holding registers, and since a
                         // thread only ever reads its own slots no barrier is involved.
                         const uint32_t ring0 = rbase + (uint32_t)tid * 8u;
-                        constexpr uint32_t kSlot = kCT * 8u, kRingMask = kRingDepth * kSlot - 1u;
+                        constexpr uint32_t kSlot = kCT * 8u;
 #pragma unroll
                         for (int j = 0; j < kRingDepth - 1; ++j) {
                             if (j < nrows) cp_async8(ring0 + (uint32_t)j * kSlot, sp + (size_t)j * rstep);
                             cp_async_commit();
                         }
                         const uint8_t* spn = sp + (size_t)(kRingDepth - 1) * rstep;
-                        uint32_t rd = 0u, wr = (uint32_t)(kRingDepth - 1) * kSlot;
-                        // two passes over one loop body: thread 0 (tr == 0, the most rows) draws the next ticket ~4 rows
-                        // before the end, which hides the atomic's round trip without a test in every iteration
-                        int i = 0;
+                        // The row loop is unrolled by the ring depth, so every ring slot is a compile-time offset (no wrap
+                        // arithmetic): row i lives in slot i % kRingDepth and is re-filled with row i + kRingDepth - 1
+                        // as soon as row i - 1 has been consumed.  Thread 0 (tr == 0, the most rows) draws the next ticket
+                        // at the start of the last round, which hides the atomic's round trip.
 #pragma unroll 1
-                        for (int pass = 0; pass < 2; ++pass) {
-                            const int iend = pass ? nrows : max(nrows - 4, 0);
-#pragma unroll 1
-                            for (; i < iend; ++i) {
-                                if (i + kRingDepth - 1 < nrows) cp_async8(ring0 + wr, spn);
-                                cp_async_commit();
-                                cp_async_wait<kRingDepth - 1>();
-                                const uint2 px = lds_u64(ring0 + rd);
-                                const uint64_t yw = lds_b64(yw_addr);
-                                const uint2 o = clahe_blend_8(px, lane8, xa, xa1, yw);
-                                __stcs(reinterpret_cast<uint2*>(dp), o);
-                                spn += rstep; dp += rstep; yw_addr += yw_step;
-                                wr = rd;
-                                rd = (rd + kSlot) & kRingMask;
+                        for (int i0 = 0; i0 < nrows; i0 += kRingDepth) {
+                            if (i0 + kRingDepth >= nrows) q.prefetch();
+#pragma unroll
+                            for (int j = 0; j < kRingDepth; ++j) {
+                                const int i = i0 + j;
+                                if (i < nrows) {
+                                    if (i + kRingDepth - 1 < nrows) cp_async8(ring0 + (uint32_t)((j + kRingDepth - 1) % kRingDepth) * kSlot, spn);
+                                    cp_async_commit();
+                                    cp_async_wait<kRingDepth - 1>();
+                                    const uint2 px = lds_u64(ring0 + (uint32_t)j * kSlot);
+                                    const uint64_t yw = lds_b64(yw_addr);
+                                    const uint2 o = clahe_blend_8(px, lane8, xa, xa1, yw);
+                                    __stcs(reinterpret_cast<uint2*>(dp), o);
+                                    spn += rstep; dp += rstep; yw_addr += yw_step;
+                                }
                             }
-                            if (pass == 0) q.prefetch();
                         }
                     }
                 }
