@@ -226,11 +226,14 @@ class SpatialSplitEqualizer:
         hist = torch.zeros(256, dtype=torch.int32, device=d_band_in.device)
         if rows > 0:
             self.ctx.hist_device(d_band_in, 1, self.width * rows, self.width, rows, hist, stream=stream)
-        if stream is not None:
-            stream.synchronize()
-        else:
+        # torch's NCCL all-reduce is ordered after the work already queued on the current torch stream; only the context's
+        # own stream (stream=None) is invisible to torch and has to be drained first
+        if stream is None:
             self.ctx.sync()
         allreduce_histograms(hist, self.group)
+        if stream is None:
+            import torch
+            torch.cuda.current_stream().synchronize()   # the all-reduce ran on torch's stream; the apply runs on ours
         if rows > 0:
             self.ctx.equalize_apply_device(d_band_in, d_band_out, 1, self.width * rows, self.width, rows, hist,
                                            self.width * self.height, stream=stream)
