@@ -19,6 +19,9 @@
  *                                          accel.cpp:36-61 (device buffers in, device buffers out)
  *   nv12eq_color_equalize / _clahe      <- cvtColor(BGR2YUV) -> split -> equalizeHist/CLAHE(Y) -> merge ->
  *                                          cvtColor(YUV2BGR), singlecolor.cpp:39-66, clahe1frame.cpp:83-102
+ *   nv12eq_*_meta                       <- the same frame body for buffers whose planes carry GstVideoMeta offsets/strides
+ *                                          (the reference reads GstVideoInfo at nextimprovement.cpp:128-129 but assumes
+ *                                          packed planes)
  *   nv12eq_bgr_to_i420 / _device        <- cvtColor(bgr, COLOR_BGR2YUV_I420) in front of the Y-plane operator,
  *                                          1frameMeasure.cpp:32-35
  *   nv12eq_get_counters                 <- the Counters struct + status tick, OpenCLequalHist.cpp:45-61,439-508
@@ -122,6 +125,21 @@ int nv12eq_equalize_hist(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, uin
 /* clip_limit <= 0 disables clipping (as in OpenCV).  tiles_x/tiles_y >= 1 (reference: --tile, default 8). */
 int nv12eq_clahe(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, uint8_t* out, size_t out_size, int width,
                  int height, int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode);
+
+/* ---- host frames described by per-plane offsets and strides (GstVideoMeta: offset[2], stride[2]) ------------------------
+ * the reference assumes stride == width and chroma at width*height (OpenCVequalHist.cpp:140);
+ * real decoders and cameras pad rows and planes.  Plane 0 is Y (height rows), plane 1 is interleaved UV (height/2 rows);
+ * the input and the output buffer may use different layouts.  Only the `width` payload bytes of every row are read or
+ * written.  A NULL layout means the packed default {0, stride*height} / {width, width}. */
+typedef struct nv12eq_layout {
+    size_t offset[2];   /* byte offset of plane 0 (Y) and plane 1 (UV) from the buffer start */
+    int stride[2];      /* bytes between rows of each plane, >= width */
+} nv12eq_layout;
+int nv12eq_equalize_hist_meta(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, const nv12eq_layout* in_layout, uint8_t* out,
+                              size_t out_size, const nv12eq_layout* out_layout, int width, int height, int uv_mode);
+int nv12eq_clahe_meta(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, const nv12eq_layout* in_layout, uint8_t* out,
+                      size_t out_size, const nv12eq_layout* out_layout, int width, int height, double clip_limit, int tiles_x,
+                      int tiles_y, int uv_mode);
 
 /* ---- host batches: n_frames frames, frame k at in + k*frame_pitch (frame_pitch >= stride*(h+h/2)) ------ */
 /* Synchronous; internally pipelined (pinned double buffering, H2D / kernels / D2H on separate streams). */

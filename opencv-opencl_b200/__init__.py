@@ -54,6 +54,14 @@ class StreamConfig(ctypes.Structure):
                 ("depth", ctypes.c_int), ("full_policy", ctypes.c_int)]
 
 
+class Layout(ctypes.Structure):
+    """nv12eq_layout: GstVideoMeta-style plane offsets and strides (plane 0 = Y, plane 1 = UV)."""
+    _fields_ = [("offset", ctypes.c_size_t * 2), ("stride", ctypes.c_int * 2)]
+
+    def __init__(self, y_offset=0, uv_offset=0, y_stride=0, uv_stride=0):
+        super().__init__((ctypes.c_size_t * 2)(y_offset, uv_offset), (ctypes.c_int * 2)(y_stride, uv_stride))
+
+
 class StreamStats(ctypes.Structure):
     _fields_ = [(k, ctypes.c_uint64) for k in ("pushed", "delivered", "dropped_backpressure", "in_flight", "max_in_flight",
                                                "latency_us_sum", "latency_us_max")]
@@ -103,6 +111,10 @@ _SIGNATURES = {
     "nv12eq_color_clahe": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int]),
     "nv12eq_color_equalize_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "nv12eq_color_clahe_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_vp]),
+    "nv12eq_equalize_hist_meta": (_c_int, [_c_vp, _c_vp, _c_sz, ctypes.POINTER(Layout), _c_vp, _c_sz, ctypes.POINTER(Layout), _c_int, _c_int,
+                                           _c_int]),
+    "nv12eq_clahe_meta": (_c_int, [_c_vp, _c_vp, _c_sz, ctypes.POINTER(Layout), _c_vp, _c_sz, ctypes.POINTER(Layout), _c_int, _c_int, _c_dbl,
+                                   _c_int, _c_int, _c_int]),
     "nv12eq_bgr_to_i420": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_sz]),
     "nv12eq_bgr_to_i420_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_sz, _c_int, _c_int, _c_int, _c_vp]),
     "nv12eq_stream_open": (_c_int, [_c_vp, ctypes.POINTER(StreamConfig), ctypes.POINTER(_c_vp)]),
@@ -276,6 +288,28 @@ class Context:
         out = np.empty_like(nv12) if out is None else out
         st = self._lib.nv12eq_clahe(self._h, _ptr(nv12), _nbytes(nv12), _ptr(out), _nbytes(out), width, height, stride,
                                     float(clip_limit), int(tiles[0]), int(tiles[1]), uv_mode)
+        if raw_status:
+            return st
+        self._check(st)
+        return out
+
+    def equalize_hist_meta(self, buf, width, height, in_layout=None, out=None, out_layout=None, uv_mode=UV_COPY, raw_status=False):
+        """Frame whose planes sit at GstVideoMeta offsets/strides (``Layout``); None = packed planes."""
+        out = np.empty_like(buf) if out is None else out
+        st = self._lib.nv12eq_equalize_hist_meta(self._h, _ptr(buf), _nbytes(buf), ctypes.byref(in_layout) if in_layout else None,
+                                                 _ptr(out), _nbytes(out), ctypes.byref(out_layout) if out_layout else None, width,
+                                                 height, uv_mode)
+        if raw_status:
+            return st
+        self._check(st)
+        return out
+
+    def clahe_meta(self, buf, width, height, clip_limit=2.0, tiles=(8, 8), in_layout=None, out=None, out_layout=None,
+                   uv_mode=UV_COPY, raw_status=False):
+        out = np.empty_like(buf) if out is None else out
+        st = self._lib.nv12eq_clahe_meta(self._h, _ptr(buf), _nbytes(buf), ctypes.byref(in_layout) if in_layout else None, _ptr(out),
+                                         _nbytes(out), ctypes.byref(out_layout) if out_layout else None, width, height,
+                                         float(clip_limit), int(tiles[0]), int(tiles[1]), uv_mode)
         if raw_status:
             return st
         self._check(st)

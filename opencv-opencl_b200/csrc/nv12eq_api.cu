@@ -1128,6 +1128,70 @@ int nv12eq_color_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_o
 }
 
 
+// ---- frames with per-plane offsets / strides -----------------------------------------------------------
+// The DMA engine does the re-layout: the luma rows are gathered into a flat device plane (so the kernels always take
+// their contiguous fast path), processed with UV_SKIP, and scattered back with the output's stride; the chroma rows are
+// copied / filled on the host like in the packed entry points.
+static int meta_frame(nv12eq_ctx* ctx, Op op, const uint8_t* in, size_t in_size, const nv12eq_layout* il, uint8_t* out, size_t out_size,
+                      const nv12eq_layout* ol, int w, int h, double clip, int tx, int ty, int uv_mode) {
+    int rc = check_geometry(ctx, w, h, w, 1, 0, uv_mode);
+    if (rc) return rc;
+    if (!in || !out) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "null frame pointer");
+    if (op == Op::Clahe && (tx < 1 || ty < 1)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", tx, ty);
+    const nv12eq_layout packed{{0, (size_t)w * h}, {w, w}};
+    const nv12eq_layout& I = il ? *il : packed;
+    const nv12eq_layout& O = ol ? *ol : packed;
+    const int uvh = h / 2;
+    for (const nv12eq_layout* L : {&I, &O})
+        if (L->stride[0] < w || L->stride[1] < w) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "plane stride smaller than the width");
+    auto plane_end = [&](const nv12eq_layout& L, int pl, int rows) { return rows > 0 ? L.offset[pl] + (size_t)L.stride[pl] * (rows - 1) + w : (size_t)0; };
+    const bool in_uv_needed = (uv_mode == UV_COPY);
+    if (plane_end(I, 0, h) > in_size || (in_uv_needed && plane_end(I, 1, uvh) > in_size) || plane_end(O, 0, h) > out_size ||
+        (uv_mode != UV_SKIP && plane_end(O, 1, uvh) > out_size))
+        return fail(ctx, NV12EQ_ERR_SHORT_BUFFER, "a plane described by the layout does not fit in its buffer");
+    const auto t0 = std::chrono::steady_clock::now();
+    DeviceGuard guard(ctx->device);
+    Lane& L = ctx->lanes[0];
+    if ((rc = lane_wait(ctx, L))) return rc;
+    const size_t plane = (size_t)w * h;
+    if ((rc = dev_reserve(ctx, L.d_in, plane, false))) return rc;
+    if ((rc = dev_reserve(ctx, L.d_out, plane, false))) return rc;
+    uint8_t* d_in = reinterpret_cast<uint8_t*>(L.d_in.p);
+    uint8_t* d_out = reinterpret_cast<uint8_t*>(L.d_out.p);
+    CK(ctx, cudaMemcpy2DAsync(d_in, (size_t)w, in + I.offset[0], (size_t)I.stride[0], (size_t)w, (size_t)h, cudaMemcpyHostToDevice, L.stream));
+    rc = (op == Op::Clahe) ? launch_clahe(ctx, L.ws, d_in, d_out, 1, plane, w, h, w, clip, tx, ty, UV_SKIP, L.stream)
+                           : launch_equalize(ctx, L.ws, d_in, d_out, 1, plane, w, h, w, UV_SKIP, L.stream);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpy2DAsync(out + O.offset[0], (size_t)O.stride[0], d_out, (size_t)w, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, L.stream));
+    // chroma on the host while the GPU works (rows may alias when in == out with identical layouts: then nothing to do)
+    if (uvh > 0 && uv_mode != UV_SKIP) {
+        const uint8_t* src = in + I.offset[1];
+        uint8_t* dst = out + O.offset[1];
+        const bool same = (uv_mode == UV_COPY && src == dst && I.stride[1] == O.stride[1]);
+        if (!same)
+            for (int r = 0; r < uvh; ++r) {
+                if (uv_mode == UV_COPY) memmove(dst + (size_t)r * O.stride[1], src + (size_t)r * I.stride[1], (size_t)w);
+                else memset(dst + (size_t)r * O.stride[1], 128, (size_t)w);
+            }
+    }
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    ctx->ctr.bytes_in += plane; ctx->ctr.bytes_out += plane; ctx->ctr.frames++;
+    ctx->ctr.busy_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    return NV12EQ_OK;
+}
+
+int nv12eq_equalize_hist_meta(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, const nv12eq_layout* in_layout, uint8_t* out,
+                              size_t out_size, const nv12eq_layout* out_layout, int width, int height, int uv_mode) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    return meta_frame(ctx, Op::Equalize, in, in_size, in_layout, out, out_size, out_layout, width, height, 0.0, 0, 0, uv_mode);
+}
+
+int nv12eq_clahe_meta(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, const nv12eq_layout* in_layout, uint8_t* out, size_t out_size,
+                      const nv12eq_layout* out_layout, int width, int height, double clip_limit, int tiles_x, int tiles_y, int uv_mode) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    return meta_frame(ctx, Op::Clahe, in, in_size, in_layout, out, out_size, out_layout, width, height, clip_limit, tiles_x, tiles_y, uv_mode);
+}
+
 // ---- BGR -> I420 adapter --------------------------------------------------------------------------------
 static int launch_i420(nv12eq_ctx* ctx, const uint8_t* d_bgr, uint8_t* d_out, int n, size_t bgr_pitch, size_t out_pitch, int w, int h,
                        int stride, cudaStream_t st) {

@@ -97,3 +97,50 @@ def test_gpu_i420_device_batch(nv, oracle):
         for k in range(n):
             want = oracle.c_bgr2i420(oracle.c_synth_bgr(W, H, k))
             assert np.array_equal(d_out[k * opitch:(k + 1) * opitch].cpu().numpy().reshape(H * 3 // 2, W), want), k
+
+
+def _lay_out(nv, planes_y, planes_uv, W, H, lay, size, fill):
+    """Place a packed NV12 frame into a buffer with the given plane offsets / strides."""
+    buf = np.full(size, fill, np.uint8)
+    for r in range(H):
+        buf[lay.offset[0] + r * lay.stride[0]: lay.offset[0] + r * lay.stride[0] + W] = planes_y[r]
+    for r in range(H // 2):
+        buf[lay.offset[1] + r * lay.stride[1]: lay.offset[1] + r * lay.stride[1] + W] = planes_uv[r]
+    return buf
+
+
+@pytest.mark.gpu
+def test_gpu_gstvideometa_layouts(nv, oracle):
+    """nv12eq_*_meta: planes at arbitrary offsets with padded rows, different layouts for
+    the input and the output buffer; payload bit-exact with the oracle, every padding byte untouched."""
+    W, H = 322, 202
+    packed = oracle.c_synth_nv12(W, H, 2026, 4)
+    y, uv = packed[:W * H].reshape(H, W), packed[W * H:].reshape(H // 2, W)
+    il = nv.Layout(y_offset=64, uv_offset=64 + 384 * H + 128, y_stride=384, uv_stride=352)
+    ol = nv.Layout(y_offset=0, uv_offset=336 * H + 32, y_stride=336, uv_stride=400)
+    in_size = il.offset[1] + il.stride[1] * (H // 2) + 17
+    out_size = ol.offset[1] + ol.stride[1] * (H // 2) + 5
+    src = _lay_out(nv, y, uv, W, H, il, in_size, 0xAB)
+    with nv.Context(0, 512, 512, 1) as ctx:
+        for op in ("eq", "clahe"):
+            for uv_mode, ouv in ((nv.UV_COPY, oracle.UV_COPY), (nv.UV_GRAY128, oracle.UV_GRAY128), (nv.UV_SKIP, oracle.UV_SKIP)):
+                want = (oracle.c_nv12_equalize_hist(packed, W, H, uv_mode=ouv, out=np.full_like(packed, 0xCD)) if op == "eq" else
+                        oracle.c_nv12_clahe(packed, W, H, 3.0, 4, 5, uv_mode=ouv, out=np.full_like(packed, 0xCD)))
+                expect = _lay_out(nv, want[:W * H].reshape(H, W), want[W * H:].reshape(H // 2, W), W, H, ol, out_size, 0xCD)
+                out = np.full(out_size, 0xCD, np.uint8)
+                if op == "eq":
+                    ctx.equalize_hist_meta(src, W, H, il, out, ol, uv_mode)
+                else:
+                    ctx.clahe_meta(src, W, H, 3.0, (4, 5), il, out, ol, uv_mode)
+                assert np.array_equal(out, expect), (op, uv_mode)
+        # packed default (NULL layouts) == the plain entry point; in place with one layout
+        assert np.array_equal(ctx.equalize_hist_meta(packed, W, H), oracle.c_nv12_equalize_hist(packed, W, H))
+        buf = src.copy()
+        ctx.equalize_hist_meta(buf, W, H, il, buf, il, nv.UV_COPY)
+        want = oracle.c_nv12_equalize_hist(packed, W, H)
+        assert np.array_equal(buf, _lay_out(nv, want[:W * H].reshape(H, W), want[W * H:].reshape(H // 2, W), W, H, il, in_size, 0xAB))
+        # error behaviour
+        bad = nv.Layout(0, W * H, W - 1, W)
+        assert ctx.equalize_hist_meta(packed, W, H, bad, raw_status=True) == nv.ERR_INVALID_ARGUMENT
+        far = nv.Layout(0, packed.size, W, W)
+        assert ctx.equalize_hist_meta(packed, W, H, far, raw_status=True) == nv.ERR_SHORT_BUFFER
