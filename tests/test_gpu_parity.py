@@ -364,3 +364,39 @@ def test_color_full_bgr_cube(nv, oracle):
         buf = small.copy()
         c.color_equalize(buf, nv.COLOR_YUV, out=buf)
         assert np.array_equal(buf, want)
+
+
+def test_randomized_geometries(nv, oracle):
+    """Seeded sweep over ragged geometries: odd widths / heights, strides with every alignment, tile grids that do not
+    divide the image (OpenCV's reflect-101 padding path), grids larger than the image, tiny frames, all uv modes, in-place
+    and batched calls.  Every result is compared bit-exactly with the oracle."""
+    rng = np.random.default_rng(20261018)
+    with nv.Context(0, 1024, 1024, 2) as c:
+        for case in range(70):
+            W = int(rng.choice([1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 33, 63, 64, 65, 120, 127, 128, 130, 240, 250, 256, 333, 480, 511, 640]))
+            H = int(rng.choice([1, 2, 3, 5, 8, 9, 16, 17, 30, 33, 64, 67, 100, 135, 136, 270, 271]))
+            S = W + int(rng.choice([0, 0, 1, 3, 5, 8, 16, 29, 32]))
+            uv_mode = int(rng.integers(0, 3))
+            nv12 = oracle.c_synth_nv12(W, H, int(rng.integers(1, 1 << 20)), int(rng.integers(0, 100)), stride=S)
+            if rng.random() < 0.2:                       # flat / two-valued frames: constant-image and i0 edge cases
+                nv12[:] = int(rng.integers(0, 256))
+                if rng.random() < 0.5 and nv12.size > 3:
+                    nv12[int(rng.integers(0, S * H))] = int(rng.integers(0, 256))
+            pre = rng.integers(0, 256, nv12.size, dtype=np.uint8)
+            got = c.equalize_hist(nv12, W, H, stride=S, uv_mode=uv_mode, out=pre.copy())
+            want = oracle.c_nv12_equalize_hist(nv12, W, H, stride=S, uv_mode=uv_mode, out=pre.copy())
+            assert np.array_equal(got, want), ("eq", case, W, H, S, uv_mode)
+            tx, ty = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 16])), int(rng.choice([1, 2, 3, 4, 6, 8, 9, 16]))
+            clip = float(rng.choice([0.0, 0.5, 1.0, 2.0, 3.0, 40.0]))
+            got = c.clahe(nv12, W, H, clip, (tx, ty), stride=S, uv_mode=uv_mode, out=pre.copy())
+            want = oracle.c_nv12_clahe(nv12, W, H, clip, tx, ty, stride=S, uv_mode=uv_mode, out=pre.copy())
+            assert np.array_equal(got, want), ("clahe", case, W, H, S, uv_mode, clip, tx, ty)
+            if case % 5 == 0:                            # in place, and a 3-frame batch of the same geometry
+                buf = nv12.copy()
+                c.clahe(buf, W, H, clip, (tx, ty), stride=S, uv_mode=nv.UV_COPY, out=buf)
+                assert np.array_equal(buf, oracle.c_nv12_clahe(nv12, W, H, clip, tx, ty, stride=S, out=nv12.copy())), ("inplace", case)
+                batch = np.stack([nv12, np.roll(nv12, 7), nv12[::-1].copy()])
+                outb = c.equalize_hist_batch(batch, W, H, stride=S, out=np.zeros_like(batch))
+                for k in range(3):
+                    wantk = oracle.c_nv12_equalize_hist(batch[k], W, H, stride=S, out=np.zeros_like(nv12))
+                    assert np.array_equal(outb[k].reshape(-1, S)[:, :W], wantk.reshape(-1, S)[:, :W]), ("batch", case, k)
