@@ -152,42 +152,51 @@ class FrameShardedStream:
     def __init__(self, streams: Sequence[Any]):
         if not streams:
             raise ValueError("need at least one stream")
+        import threading
         self.streams = list(streams)
         self.world = len(self.streams)
         self._push_seq = 0
         self._pop_seq = 0
         self._local: Dict[int, Optional[int]] = {}   # global seq -> per-stream seq (None = dropped)
         self.dropped = 0
+        self._cv = threading.Condition()              # one producer thread may push while one consumer thread pops
 
     def push(self, frame) -> Optional[int]:
         k = self._push_seq
-        self._push_seq += 1
-        local = self.streams[stream_owner(k, self.world)].push(frame)
-        self._local[k] = local
-        if local is None:
-            self.dropped += 1
-            return None
-        return k
+        local = self.streams[stream_owner(k, self.world)].push(frame)   # may block (FULL_BLOCK): outside the lock
+        with self._cv:
+            self._local[k] = local
+            self._push_seq = k + 1
+            if local is None:
+                self.dropped += 1
+            self._cv.notify_all()
+        return None if local is None else k
 
-    def pop(self, out=None, block: bool = True):
-        """Next frame in capture order: (global_seq, frame), or None when nothing is pending / ready."""
-        while self._pop_seq < self._push_seq:
-            k = self._pop_seq
-            local = self._local.get(k)
-            if local is None:          # dropped at push time
-                self._local.pop(k, None)
-                self._pop_seq += 1
-                continue
+    def pop(self, out=None, block: bool = True, wait_push: bool = False):
+        """Next frame in capture order: (global_seq, frame).  None when nothing has been pushed that is not yet popped
+        (unless wait_push: then wait for the producer thread), or when block=False and the frame is not finished."""
+        while True:
+            with self._cv:
+                while self._pop_seq >= self._push_seq:
+                    if not wait_push:
+                        return None
+                    self._cv.wait()
+                k = self._pop_seq
+                local = self._local.pop(k)
+                if local is None:          # dropped at push time: skip the gap
+                    self._pop_seq += 1
+                    continue
             got = self.streams[stream_owner(k, self.world)].pop(out=out, block=block)
-            if got is None:
+            if got is None:                # not finished yet (block=False): put the bookkeeping back
+                with self._cv:
+                    self._local[k] = local
                 return None
             seq, frame = got
-            if seq > local:            # the owner discarded frame k (drop-oldest) and delivered a later one
+            if seq > local:                # the owner discarded frame k (drop-oldest) and delivered a later one
                 raise RuntimeError("per-GPU stream skipped ahead; use FULL_BLOCK or FULL_DROP_NEWEST with FrameShardedStream")
-            self._local.pop(k, None)
-            self._pop_seq += 1
+            with self._cv:
+                self._pop_seq += 1
             return k, frame
-        return None
 
     def pending(self) -> int:
         return self._push_seq - self._pop_seq

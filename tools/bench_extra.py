@@ -73,7 +73,7 @@ def color(args):
 def stream(args):
     from oracle import oracle as O
     W, H = SIZES[args.size]
-    ctx = nv12eq.Context(0, W, H, 1)
+    ctxs = [nv12eq.Context(g, W, H, 1) for g in range(args.gpus)]   # one context per GPU, one process (config 4 shape)
     op = nv12eq.OP_CLAHE if args.op == "clahe" else nv12eq.OP_EQUALIZE
     frames = [O.c_synth_nv12(W, H, 2026, k) for k in range(8)]
     want = [O.c_nv12_clahe(f, W, H, args.clip, args.tiles, args.tiles) if args.op == "clahe" else O.c_nv12_equalize_hist(f, W, H)
@@ -81,9 +81,10 @@ def stream(args):
     n = args.frames
     res = {}
     for label, fps in (("paced", args.fps), ("unpaced", 0)):
-        s = nv12eq.Stream(ctx, W, H, op=op, clip_limit=args.clip, tiles=(args.tiles, args.tiles), depth=args.depth,
-                          full_policy=nv12eq.FULL_BLOCK)
-        lat, bad, out = [], [0], np.empty(s.frame_bytes, np.uint8)
+        subs = [nv12eq.Stream(c, W, H, op=op, clip_limit=args.clip, tiles=(args.tiles, args.tiles), depth=args.depth,
+                              full_policy=nv12eq.FULL_BLOCK) for c in ctxs]
+        s = subs[0] if len(subs) == 1 else nv12eq.sharding.FrameShardedStream(subs)   # frame k -> GPU k mod N, in-order pop
+        lat, bad, out = [], [0], np.empty(subs[0].frame_bytes, np.uint8)
         t_push = {}
 
         def producer():
@@ -98,7 +99,7 @@ def stream(args):
 
         def consumer():
             for k in range(n):
-                q, f = s.pop(out=out, block=True)
+                q, f = s.pop(out=out, block=True, wait_push=True) if len(subs) > 1 else s.pop(out=out, block=True)
                 lat.append(time.perf_counter() - t_push[q])
                 if q != k or (k % 16 == 0 and not np.array_equal(f, want[q % 8])):
                     bad[0] += 1
@@ -106,14 +107,16 @@ def stream(args):
         t0 = time.perf_counter()
         tp.start(); tc.start(); tp.join(); tc.join()
         dt = time.perf_counter() - t0
-        st = s.stats()
+        sts = [x.stats() for x in subs]
+        st = {"max_in_flight": sum(x["max_in_flight"] for x in sts), "dropped_backpressure": sum(x["dropped_backpressure"] for x in sts)}
         s.close()
         lat_ms = np.array(lat) * 1e3
         res[label] = {"target_fps": fps or None, "frames_per_sec": n / dt, "latency_ms_p50": float(np.percentile(lat_ms, 50)),
                       "latency_ms_p99": float(np.percentile(lat_ms, 99)), "latency_ms_max": float(lat_ms.max()),
                       "in_order_and_bit_exact": bad[0] == 0, "max_in_flight": st["max_in_flight"], "dropped": st["dropped_backpressure"]}
     print(json.dumps({"metric": "nv12_stream", "config": {"workload": f"{args.op} on a {W}x{H} NV12 stream through nv12eq_stream_* "
-                                                                      f"(host frames in, host frames out, depth {args.depth})",
+                                                                      f"(host frames in, host frames out, depth {args.depth} per GPU, "
+                                                                      f"{args.gpus} GPU(s) in one process, frame k -> GPU k mod N)",
                                                           "frames": n}, **res}))
 
 
@@ -129,6 +132,7 @@ def main():
     ap.add_argument("--color-mode", default="yuv", choices=["yuv", "ycrcb"])
     ap.add_argument("--fps", type=float, default=60.0)
     ap.add_argument("--depth", type=int, default=4)
+    ap.add_argument("--gpus", type=int, default=1, help="stream mode: GPUs driven by this one process")
     args = ap.parse_args()
     nv12eq.build()
     (color if args.what == "color" else stream)(args)
