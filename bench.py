@@ -185,6 +185,7 @@ def calibrate_cpu_frames(args, W, H, target_s, passes):
     per_frame = max(time.perf_counter() - t0, 1e-4)
     n = int(target_s / passes / per_frame * min(cores, 16))
     n = max(min(cores, 128), min(n, 128))
+    calibrate_cpu_frames.per_frame_s = per_frame   # single-thread seconds per frame, for sizing the number of passes
     return max(4, n)
 
 
@@ -356,7 +357,10 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         nf = calibrate_cpu_frames(args, W, H, args.cpu_seconds, 3)
-        r = cpu_leg(args, W, H, nf, 2, 1)
+        # about --cpu-seconds (default 12) of CPU work in total: the frame count is capped by host memory, so the number of
+        # passes over the sample makes up the rest
+        passes = int(max(2, min(40, round(args.cpu_seconds / (nf * calibrate_cpu_frames.per_frame_s)))))
+        r = cpu_leg(args, W, H, nf, passes, 1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {
