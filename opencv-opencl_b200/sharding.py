@@ -207,6 +207,48 @@ class FrameShardedStream:
 
 
 # ------------------------------------------------------------------------------------------------------------
+# one process, several GPUs: a host batch cut into contiguous slices, one slice per GPU, no collective
+# ------------------------------------------------------------------------------------------------------------
+class ShardedBatch:
+    """Frame-sharded batch processing over several contexts (one per GPU) from ONE process: rank r of N gets the
+    contiguous slice `shard_range(n_frames, r, N)` of the host batch and runs it through its own context on its own host
+    thread (the C calls release the GIL), so uploads, kernels and downloads of all GPUs overlap.  The N-process form of
+    the same partition is what bench.py runs under torchrun."""
+
+    def __init__(self, contexts: Sequence[Any]):
+        if not contexts:
+            raise ValueError("need at least one context")
+        from concurrent.futures import ThreadPoolExecutor
+        self.contexts = list(contexts)
+        self.world = len(self.contexts)
+        self._pool = ThreadPoolExecutor(max_workers=self.world)
+
+    def _run(self, method: str, frames, out, n_frames: int, frame_pitch: int, width: int, height: int, **kw):
+        import numpy as np
+        flat_in = np.asarray(frames).reshape(-1)
+        flat_out = np.asarray(out).reshape(-1)
+
+        def one(rank):
+            start, count = shard_range(n_frames, rank, self.world)
+            if count == 0:
+                return
+            a, b = start * frame_pitch, (start + count) * frame_pitch
+            getattr(self.contexts[rank], method)(flat_in[a:b], width, height, out=flat_out[a:b], n_frames=count,
+                                                 frame_pitch=frame_pitch, **kw)
+        list(self._pool.map(one, range(self.world)))   # re-raises the first worker exception
+        return out
+
+    def equalize_hist(self, frames, width, height, out, n_frames, frame_pitch, **kw):
+        return self._run("equalize_hist_batch", frames, out, n_frames, frame_pitch, width, height, **kw)
+
+    def clahe(self, frames, width, height, out, n_frames, frame_pitch, clip_limit=2.0, tiles=(8, 8), **kw):
+        return self._run("clahe_batch", frames, out, n_frames, frame_pitch, width, height, clip_limit=clip_limit, tiles=tiles, **kw)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
 # optional spatial split of one frame: the only collective on the path
 # ------------------------------------------------------------------------------------------------------------
 def allreduce_histograms(hist, group=None):

@@ -168,3 +168,24 @@ def test_cpp_example_runs_both_modes(nv):
                              capture_output=True, text=True, timeout=120)
         assert out.returncode == 0, out.stdout + out.stderr
         assert "processed 24, delivered in order 24, out of order 0, errors 0" in out.stdout, out.stdout
+
+
+def test_sharded_batch_over_contexts(nv, oracle):
+    """One process, N contexts (one per visible GPU; two on the same GPU when only one is visible): contiguous slices of a
+    host batch, no collective, results identical to the single-context batch."""
+    import torch
+    W, H, n = 640, 360, 11
+    devs = list(range(torch.cuda.device_count())) if torch.cuda.device_count() > 1 else [0, 0]
+    ctxs = [nv.Context(d, W, H, 2) for d in devs]
+    sb = nv.sharding.ShardedBatch(ctxs)
+    frames = np.stack([oracle.c_synth_nv12(W, H, 9, k) for k in range(n)])
+    pitch = frames.shape[1]
+    out = np.zeros_like(frames)
+    sb.equalize_hist(frames, W, H, out, n, pitch)
+    assert np.array_equal(out, oracle.c_nv12_batch("equalize", frames, W, H))
+    out2 = np.zeros_like(frames)
+    sb.clahe(frames, W, H, out2, n, pitch, clip_limit=2.0, tiles=(8, 8), uv_mode=nv.UV_GRAY128)
+    assert np.array_equal(out2, oracle.c_nv12_batch("clahe", frames, W, H, clip=2.0, tx=8, ty=8, uv_mode=oracle.UV_GRAY128))
+    sb.close()
+    for c in ctxs:
+        c.close()
