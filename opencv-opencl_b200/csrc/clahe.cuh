@@ -227,7 +227,7 @@ __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint3
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 // eight horizontally adjacent pixels (two packed words) -> two packed output words
-__device__ __forceinline__ uint2 clahe_blend_8(uint2 px, uint32_t lane8, const float (&xa)[8], const float (&xa1)[8], uint64_t yw) {
+__device__ __forceinline__ uint2 clahe_blend_8(uint2 px, uint32_t lane8, const float* xa, const float* xa1, uint64_t yw) {
     // re-read the table base here: a fresh uniform value lets ptxas address the gathers as [R + UR] instead of adding
     // a base held in a vector register to every offset
     const uint32_t tbase = smem_u32(nv12eq_smem_rows);
@@ -254,6 +254,55 @@ __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float&
 }
 // keeps a value in its register: stops the compiler from re-deriving xa1 = 1 - xa inside the pixel loop
 __device__ __forceinline__ void pin_register(float& v) { asm volatile("" : "+f"(v)); }
+
+// The rows of one thread inside a cell: G (8 or 16) horizontally adjacent pixels per row, rows tr, tr + rpp, ...
+// Thread-private ring of D G-byte slots in shared memory, filled with cp.async: the rows D-1 ahead are in flight
+// (about 50 KB per SM) without holding registers, and since a thread only ever reads its own slots no barrier is
+// involved.  The row loop is unrolled by the ring depth, so every ring slot is a compile-time offset.  Thread 0
+// (tr == 0, the most rows) draws the next ticket at the start of the last round, which hides the atomic's round trip.
+// G = 16 halves the per-row overhead (ring, pointers, y weights, loop) per pixel; it needs 32 registers of x weights.
+template <int G>
+__device__ __forceinline__ void clahe_cell_rows(TicketQueue& q, const uint8_t* sp, uint8_t* dp, size_t rstep, int nrows, int xg, float inv_tw,
+                                                uint32_t ring0, uint32_t yw_addr, uint32_t yw_step, uint32_t lane8) {
+    constexpr int D = (G == 16) ? kRingDepth / 2 : kRingDepth;   // same ring bytes either way
+    constexpr uint32_t kSlot = kCT * G;
+    float xa[G], xa1[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) axis_weight(xg + k, inv_tw, xa[k], xa1[k]);
+    auto issue = [&](uint32_t slot, const uint8_t* g) {
+        if (G == 16) cp_async16(ring0 + slot * kSlot, g); else cp_async8(ring0 + slot * kSlot, g);
+    };
+#pragma unroll
+    for (int j = 0; j < D - 1; ++j) {
+        if (j < nrows) issue((uint32_t)j, sp + (size_t)j * rstep);
+        cp_async_commit();
+    }
+    const uint8_t* spn = sp + (size_t)(D - 1) * rstep;
+#pragma unroll 1
+    for (int i0 = 0; i0 < nrows; i0 += D) {
+        if (i0 + D >= nrows) q.prefetch();
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const int i = i0 + j;
+            if (i < nrows) {
+                if (i + D - 1 < nrows) issue((uint32_t)((j + D - 1) % D), spn);
+                cp_async_commit();
+                cp_async_wait<D - 1>();
+                const uint64_t yw = lds_b64(yw_addr);
+                if (G == 16) {
+                    const int4 px = lds_s4(ring0 + (uint32_t)j * kSlot);
+                    const uint2 o0 = clahe_blend_8(make_uint2((uint32_t)px.x, (uint32_t)px.y), lane8, xa, xa1, yw);
+                    const uint2 o1 = clahe_blend_8(make_uint2((uint32_t)px.z, (uint32_t)px.w), lane8, xa + 8 * (G / 16), xa1 + 8 * (G / 16), yw);
+                    __stcs(reinterpret_cast<uint4*>(dp), make_uint4(o0.x, o0.y, o1.x, o1.y));
+                } else {
+                    const uint2 px = lds_u64(ring0 + (uint32_t)j * kSlot);
+                    __stcs(reinterpret_cast<uint2*>(dp), clahe_blend_8(px, lane8, xa, xa1, yw));
+                }
+                spn += rstep; dp += rstep; yw_addr += yw_step;
+            }
+        }
+    }
+}
 
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams p) {
@@ -401,60 +450,27 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 }
                 __syncthreads();
                 const uint32_t ywbase = smem_u32(s_yw);
-                // Fast path: full 8-pixel groups, one 8-byte load / store per thread and row.  Columns left over when the cell
-                // width is not a multiple of 8 (and everything when alignment does not allow 8-byte accesses) take the
-                // pixel-at-a-time path below.
-                const bool fast = ((xc.x & 7) == 0) && ((p.stride & 7) == 0) && ((((uintptr_t)src | (uintptr_t)dst) & 7) == 0) &&
-                                  (cw >> 3) >= 1 && (cw >> 3) <= kCT;
-                const int gpr = fast ? (cw >> 3) : 0;   // 8-pixel groups per row
-                const int xslow = xc.x + gpr * 8;        // first column of the pixel-at-a-time path
-                if (fast && !(p.debug_skip & 2)) {
+                // Fast path: full groups of G = 16 (or 8) pixels, one 16- (8-) byte load / store per thread and row.  Columns
+                // left over when the cell width is not a multiple of G (and everything when alignment does not allow vector
+                // accesses) take the pixel-at-a-time path below.
+                const uintptr_t align_or = (uintptr_t)src | (uintptr_t)dst | (uintptr_t)p.stride | (uintptr_t)xc.x;
+                const bool fast16 = ((align_or & 15) == 0) && (cw & 15) == 0 && (cw >> 4) >= 1 && (cw >> 4) <= kCT;
+                const bool fast8 = !fast16 && ((align_or & 7) == 0) && (cw >> 3) >= 1 && (cw >> 3) <= kCT;
+                const int G = fast16 ? 16 : 8;
+                const int gpr = fast16 ? (cw >> 4) : (fast8 ? (cw >> 3) : 0);   // G-pixel groups per row
+                const int xslow = xc.x + gpr * G;                               // first column of the pixel-at-a-time path
+                if (gpr > 0 && !(p.debug_skip & 2)) {
                     const int rpp = kCT / gpr;
                     const int tr = tid / gpr, tc = tid - tr * gpr;
-                    const int xg = xc.x + tc * 8;
+                    const int xg = xc.x + tc * G;
                     if (tr < rpp && tr < ch) {
-                        float xa[8], xa1[8];
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) axis_weight(xg + k, p.inv_tw, xa[k], xa1[k]);
                         const size_t rstep = (size_t)rpp * p.stride;
                         const int nrows = (ch - tr + rpp - 1) / rpp;  // rows of this thread: tr, tr + rpp, ...
                         const uint8_t* sp = src + (size_t)(yc.x + tr) * p.stride + xg;
                         uint8_t* dp = dst + (size_t)(yc.x + tr) * p.stride + xg;
-                        uint32_t yw_addr = ywbase + (uint32_t)tr * 8u;
-                        const uint32_t yw_step = (uint32_t)rpp * 8u;
-                        // Thread-private ring of kRingDepth 8-byte slots in shared memory, filled with cp.async: the rows
-                        // kRingDepth-1 ahead are in flight (about 60 KB per SM) without holding registers, and since a
-                        // thread only ever reads its own slots no barrier is involved.
-                        const uint32_t ring0 = rbase + (uint32_t)tid * 8u;
-                        constexpr uint32_t kSlot = kCT * 8u;
-#pragma unroll
-                        for (int j = 0; j < kRingDepth - 1; ++j) {
-                            if (j < nrows) cp_async8(ring0 + (uint32_t)j * kSlot, sp + (size_t)j * rstep);
-                            cp_async_commit();
-                        }
-                        const uint8_t* spn = sp + (size_t)(kRingDepth - 1) * rstep;
-                        // The row loop is unrolled by the ring depth, so every ring slot is a compile-time offset (no wrap
-                        // arithmetic): row i lives in slot i % kRingDepth and is re-filled with row i + kRingDepth - 1
-                        // as soon as row i - 1 has been consumed.  Thread 0 (tr == 0, the most rows) draws the next ticket
-                        // at the start of the last round, which hides the atomic's round trip.
-#pragma unroll 1
-                        for (int i0 = 0; i0 < nrows; i0 += kRingDepth) {
-                            if (i0 + kRingDepth >= nrows) q.prefetch();
-#pragma unroll
-                            for (int j = 0; j < kRingDepth; ++j) {
-                                const int i = i0 + j;
-                                if (i < nrows) {
-                                    if (i + kRingDepth - 1 < nrows) cp_async8(ring0 + (uint32_t)((j + kRingDepth - 1) % kRingDepth) * kSlot, spn);
-                                    cp_async_commit();
-                                    cp_async_wait<kRingDepth - 1>();
-                                    const uint2 px = lds_u64(ring0 + (uint32_t)j * kSlot);
-                                    const uint64_t yw = lds_b64(yw_addr);
-                                    const uint2 o = clahe_blend_8(px, lane8, xa, xa1, yw);
-                                    __stcs(reinterpret_cast<uint2*>(dp), o);
-                                    spn += rstep; dp += rstep; yw_addr += yw_step;
-                                }
-                            }
-                        }
+                        const uint32_t yw_addr = ywbase + (uint32_t)tr * 8u, yw_step = (uint32_t)rpp * 8u;
+                        if (fast16) clahe_cell_rows<16>(q, sp, dp, rstep, nrows, xg, p.inv_tw, rbase + (uint32_t)tid * 16u, yw_addr, yw_step, lane8);
+                        else clahe_cell_rows<8>(q, sp, dp, rstep, nrows, xg, p.inv_tw, rbase + (uint32_t)tid * 8u, yw_addr, yw_step, lane8);
                     }
                 }
                 if (xslow < xc.y && !(p.debug_skip & 2)) {
