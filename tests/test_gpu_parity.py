@@ -400,3 +400,29 @@ def test_randomized_geometries(nv, oracle):
                 for k in range(3):
                     wantk = oracle.c_nv12_equalize_hist(batch[k], W, H, stride=S, out=np.zeros_like(nv12))
                     assert np.array_equal(outb[k].reshape(-1, S)[:, :W], wantk.reshape(-1, S)[:, :W]), ("batch", case, k)
+
+
+def test_large_frames_many_frames_and_fine_grids(nv, oracle, torch):
+    """Size extremes: an 8K luma plane (33 M pixels, 518 K-pixel tiles, 960-pixel cells), a 64x64 tile grid on 1080p (tiny
+    30x17 tiles, 4225 interpolation cells), a 1x1 grid, and a 1500-frame batch of small frames in one launch."""
+    with nv.Context(0, 7680, 4320, 2) as c:
+        W, H = 7680, 4320
+        f8k = oracle.c_synth_nv12(W, H, 2026, 3)
+        assert np.array_equal(c.equalize_hist(f8k, W, H), oracle.c_nv12_equalize_hist(f8k, W, H))
+        assert np.array_equal(c.clahe(f8k, W, H, 2.0, (8, 8)), oracle.c_nv12_clahe(f8k, W, H, 2.0, 8, 8))
+        W, H = 1920, 1080
+        f = oracle.c_synth_nv12(W, H, 2026, 5)
+        for (tx, ty) in ((64, 64), (1, 1), (37, 3)):
+            assert np.array_equal(c.clahe(f, W, H, 4.0, (tx, ty)), oracle.c_nv12_clahe(f, W, H, 4.0, tx, ty)), (tx, ty)
+        W, H, n = 64, 48, 1500
+        pitch = nv.nv12_frame_bytes(W, H)
+        st = torch.cuda.current_stream()
+        d_in = torch.empty(n * pitch, dtype=torch.uint8, device="cuda")
+        d_eq, d_cl = torch.zeros_like(d_in), torch.zeros_like(d_in)
+        c.synth_nv12_device(d_in, n, pitch, W, H, seed=2026, first_frame=0, stream=st)
+        c.equalize_hist_device(d_in, d_eq, n, pitch, W, H, stream=st)
+        c.clahe_device(d_in, d_cl, n, pitch, W, H, 2.0, (8, 8), stream=st)
+        torch.cuda.synchronize()
+        h_in, h_eq, h_cl = d_in.cpu().numpy().reshape(n, pitch), d_eq.cpu().numpy().reshape(n, pitch), d_cl.cpu().numpy().reshape(n, pitch)
+        assert np.array_equal(h_eq, oracle.c_nv12_batch("equalize", h_in, W, H))
+        assert np.array_equal(h_cl, oracle.c_nv12_batch("clahe", h_in, W, H, clip=2.0, tx=8, ty=8))
