@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--lag", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--schedule", type=int, default=0)
+    ap.add_argument("--slots", type=int, default=2, help="host lanes of the context (e2e leg pipelining depth)")
     return ap.parse_args()
 
 
@@ -233,7 +234,7 @@ def run_ours(args):
     n = args.frames
     pitch = nv12eq.nv12_frame_bytes(W, H)
     bytes_per_frame_algo = 3 * W * H  # read NV12 once + write NV12 once
-    ctx = nv12eq.Context(device=local, max_width=W, max_height=H, slots=2)
+    ctx = nv12eq.Context(device=local, max_width=W, max_height=H, slots=args.slots)
     ctx.set_tuning(args.chunks, args.lag, args.ctas, args.schedule)
     stream = torch.cuda.current_stream()
     d_in = torch.empty(n * pitch, dtype=torch.uint8, device="cuda")

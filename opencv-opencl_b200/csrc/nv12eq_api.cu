@@ -799,7 +799,8 @@ int run_batch(nv12eq_ctx* ctx, Job j) {
     if (rc) return rc;
     DeviceGuard guard(ctx->device);
     const int nl = (int)ctx->lanes.size();
-    const size_t target = 64ull << 20;
+    size_t target = 64ull << 20;   // bytes per group: large enough to amortise the per-group calls, small enough to pipeline
+    if (const char* e = getenv("NV12EQ_GROUP_MB")) target = (size_t)std::max(1, atoi(e)) << 20;
     int group = (int)std::max<size_t>(1, std::min<size_t>(64, target / std::max<size_t>(1, j.pitch)));
     if (j.n <= group) group = std::max(1, (j.n + std::min(nl, j.n) - 1) / std::max(1, std::min(nl, j.n)));
     int k = 0, first_err = NV12EQ_OK;
