@@ -22,6 +22,8 @@
  *   nv12eq_*_meta                       <- the same frame body for buffers whose planes carry GstVideoMeta offsets/strides
  *                                          (the reference reads GstVideoInfo at nextimprovement.cpp:128-129 but assumes
  *                                          packed planes)
+ *   nv12eq_clahe16* / nv12eq_p010_clahe <- cv::CLAHE::apply on CV_16UC1 (65536 bins), the 16-bit path of clahevideo.cpp:195's
+ *                                          operator for P010 decoders
  *   nv12eq_bgr_to_i420 / _device        <- cvtColor(bgr, COLOR_BGR2YUV_I420) in front of the Y-plane operator,
  *                                          1frameMeasure.cpp:32-35
  *   nv12eq_get_counters                 <- the Counters struct + status tick, OpenCLequalHist.cpp:45-61,439-508
@@ -196,6 +198,18 @@ int nv12eq_color_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_bgr_in, uint8_t*
 int nv12eq_bgr_to_i420(nv12eq_ctx* ctx, const uint8_t* bgr, int width, int height, int stride, uint8_t* out, size_t out_size);
 int nv12eq_bgr_to_i420_device(nv12eq_ctx* ctx, const uint8_t* d_bgr, uint8_t* d_out, int n_frames, size_t bgr_pitch,
                               size_t out_pitch, int width, int height, int stride, void* cuda_stream);
+
+/* ---- 16-bit planes: CLAHE on CV_16UC1 (P010 / 16-bit, histSize 65536) -------------------
+ * cv::CLAHE::apply accepts CV_16UC1 with 65536-bin tile histograms; the reference only calls it on 8-bit Y planes
+ * (clahevideo.cpp:195), so this is a widening row.  Strides and pitches of the 16-bit forms are in ELEMENTS (uint16). */
+int nv12eq_clahe16_device(nv12eq_ctx* ctx, const uint16_t* d_in, uint16_t* d_out, int n_planes, size_t plane_pitch, int width,
+                          int height, int stride, double clip_limit, int tiles_x, int tiles_y, void* cuda_stream);
+int nv12eq_clahe16(nv12eq_ctx* ctx, const uint16_t* in, uint16_t* out, int width, int height, int stride, double clip_limit,
+                   int tiles_x, int tiles_y);
+/* P010 frame (10-bit samples in the high bits of 16-bit words): `height` rows of Y then `height/2` rows of interleaved UV,
+ * `stride` BYTES apart (>= 2*width).  Y goes through the 16-bit CLAHE; chroma per uv_mode (GRAY128 writes 0x8000). */
+int nv12eq_p010_clahe(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, uint8_t* out, size_t out_size, int width, int height,
+                      int stride, double clip_limit, int tiles_x, int tiles_y, int uv_mode);
 
 /* ---- ordered, back-pressured frame stream -------------------------------- */
 /* A stream is the reference's worker queue as one object: frames are pushed in capture order, run on `depth` slots

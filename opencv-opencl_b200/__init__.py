@@ -115,6 +115,9 @@ _SIGNATURES = {
                                            _c_int]),
     "nv12eq_clahe_meta": (_c_int, [_c_vp, _c_vp, _c_sz, ctypes.POINTER(Layout), _c_vp, _c_sz, ctypes.POINTER(Layout), _c_int, _c_int, _c_dbl,
                                    _c_int, _c_int, _c_int]),
+    "nv12eq_clahe16_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_vp]),
+    "nv12eq_clahe16": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int]),
+    "nv12eq_p010_clahe": (_c_int, [_c_vp, _c_vp, _c_sz, _c_vp, _c_sz, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_int]),
     "nv12eq_bgr_to_i420": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_sz]),
     "nv12eq_bgr_to_i420_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_sz, _c_int, _c_int, _c_int, _c_vp]),
     "nv12eq_stream_open": (_c_int, [_c_vp, ctypes.POINTER(StreamConfig), ctypes.POINTER(_c_vp)]),
@@ -419,6 +422,34 @@ class Context:
         self._check(self._lib.nv12eq_color_clahe_device(self._h, _ptr(d_in), _ptr(d_out), n_frames, frame_pitch, width,
                                                         height, stride, color_mode, float(clip_limit), int(tiles[0]),
                                                         int(tiles[1]), _stream_ptr(stream)))
+
+    # -- 16-bit CLAHE (CV_16UC1 / P010) ----------------------------------------------------------------
+    def clahe16(self, plane: np.ndarray, clip_limit: float = 2.0, tiles: Tuple[int, int] = (8, 8), out=None) -> np.ndarray:
+        """``cv2.createCLAHE(clip, tiles).apply`` on a (H, W) uint16 plane (65536-bin path)."""
+        assert plane.dtype == np.uint16 and plane.ndim == 2
+        h, w = plane.shape
+        out = np.empty_like(plane) if out is None else out
+        self._check(self._lib.nv12eq_clahe16(self._h, _ptr(plane), _ptr(out), w, h, plane.strides[0] // 2, float(clip_limit),
+                                             int(tiles[0]), int(tiles[1])))
+        return out
+
+    def clahe16_device(self, d_in, d_out, n_planes, plane_pitch, width, height, clip_limit=2.0, tiles=(8, 8), stride=None,
+                       stream=None):
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_clahe16_device(self._h, _ptr(d_in), _ptr(d_out), n_planes, plane_pitch, width, height, stride,
+                                                    float(clip_limit), int(tiles[0]), int(tiles[1]), _stream_ptr(stream)))
+
+    def p010_clahe(self, frame, width, height, clip_limit=2.0, tiles=(8, 8), stride=None, uv_mode=UV_COPY, out=None,
+                   raw_status=False):
+        """P010 frame (bytes): Y through the 16-bit CLAHE, chroma per uv_mode.  stride in bytes (default 2*width)."""
+        stride = 2 * width if stride is None else stride
+        out = np.empty_like(frame) if out is None else out
+        st = self._lib.nv12eq_p010_clahe(self._h, _ptr(frame), _nbytes(frame), _ptr(out), _nbytes(out), width, height, stride,
+                                         float(clip_limit), int(tiles[0]), int(tiles[1]), uv_mode)
+        if raw_status:
+            return st
+        self._check(st)
+        return out
 
     # -- BGR -> I420 adapter ---------------------------------------------------------------------------
     def bgr_to_i420(self, bgr: np.ndarray, out=None) -> np.ndarray:

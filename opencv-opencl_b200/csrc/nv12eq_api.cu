@@ -30,6 +30,7 @@
 
 #include "../../include/nv12eq.h"
 #include "clahe.cuh"
+#include "clahe16.cuh"
 #include "color.cuh"
 #include "equalize.cuh"
 
@@ -67,6 +68,8 @@ struct Workspace {
     DevBuf luts;      // clahe: [frames][tiles][256] u8
     DevBuf cells;     // clahe: int4 xcells[], ycells[]
     DevBuf luma;      // colour: [2][frames][h][w]
+    DevBuf hist16;    // clahe16: [planes][tiles][65536] u32, kept zero between launches
+    DevBuf luts16;    // clahe16: [planes][tiles][65536] u16
     int frames_cap = 0;
     // cached CLAHE geometry
     int gw = 0, gh = 0, gtx = 0, gty = 0, nxc = 0, nyc = 0;
@@ -245,7 +248,7 @@ void host_release(HostBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap
 
 void ws_release(Workspace& w) {
     dev_release(w.hist); dev_release(w.counters); dev_release(w.misc); dev_release(w.luts); dev_release(w.cells);
-    dev_release(w.luma);
+    dev_release(w.luma); dev_release(w.hist16); dev_release(w.luts16);
     w.frames_cap = 0; w.gw = w.gh = w.gtx = w.gty = 0;
 }
 
@@ -1191,6 +1194,120 @@ int nv12eq_clahe_meta(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, const 
                       const nv12eq_layout* out_layout, int width, int height, double clip_limit, int tiles_x, int tiles_y, int uv_mode) {
     if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
     return meta_frame(ctx, Op::Clahe, in, in_size, in_layout, out, out_size, out_layout, width, height, clip_limit, tiles_x, tiles_y, uv_mode);
+}
+
+// ---- 16-bit CLAHE ---------------------------------------------------------------------------------------
+static int launch_clahe16(nv12eq_ctx* ctx, Workspace& ws, const uint16_t* d_in, uint16_t* d_out, int n, size_t pitch, int w, int h,
+                          int stride, double clip, int tx, int ty, cudaStream_t st) {
+    if (n == 0) return NV12EQ_OK;
+    if (tx < 1 || ty < 1 || (long long)tx * ty > 4096) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad 16-bit tile grid %dx%d (at most 4096 tiles)", tx, ty);
+    const int T = tx * ty;
+    int extW = w, extH = h;
+    if (w % tx != 0 || h % ty != 0) { extW = w + (tx - (w % tx)); extH = h + (ty - (h % ty)); }
+    Clahe16Params p{};
+    p.w = w; p.h = h; p.stride = stride; p.pitch = pitch;
+    p.tx = tx; p.ty = ty; p.tw = extW / tx; p.th = extH / ty;
+    const int area = p.tw * p.th;
+    p.clip_limit = clip > 0.0 ? std::max(1, (int)(clip * area / 65536.0)) : 0;
+    p.lut_scale = 65535.0f / (float)area;
+    p.inv_tw = 1.0f / (float)p.tw; p.inv_th = 1.0f / (float)p.th;
+    // planes per pass: histograms are 256 KB per tile; keep the workspace near 256 MB
+    const int group = std::max(1, std::min(n, 1024 / T));
+    int rc = dev_reserve(ctx, ws.hist16, (size_t)group * T * kBins16 * sizeof(uint32_t), true);
+    if (rc) return rc;
+    if ((rc = dev_reserve(ctx, ws.luts16, (size_t)group * T * kBins16 * sizeof(uint16_t), false))) return rc;
+    p.hist = reinterpret_cast<uint32_t*>(ws.hist16.p);
+    p.luts = reinterpret_cast<uint16_t*>(ws.luts16.p);
+    for (int g0 = 0; g0 < n; g0 += group) {
+        const int ng = std::min(group, n - g0);
+        p.in = d_in + (size_t)g0 * pitch; p.out = d_out + (size_t)g0 * pitch; p.n_planes = ng;
+        p.strips = (int)std::max<long long>(1, std::min<long long>(p.th, ((long long)ctx->sm_count * 8 + (long long)T * ng - 1) / ((long long)T * ng)));
+        clahe16_hist_kernel<<<dim3(p.strips, T, ng), kC16Threads, 0, st>>>(p);
+        clahe16_lut_kernel<<<dim3(T, ng), kC16LutThreads, 0, st>>>(p);
+        const int gx = std::max(1, std::min((w + kC16Threads - 1) / kC16Threads, 64));
+        clahe16_interp_kernel<<<dim3(gx, h, ng), kC16Threads, 0, st>>>(p);
+        ctx->ctr.kernel_launches += 3;
+        CK(ctx, cudaGetLastError());
+    }
+    return NV12EQ_OK;
+}
+
+static int check_plane16(nv12eq_ctx* ctx, int w, int h, int stride, int tx, int ty) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (w <= 0 || h <= 0 || stride < w) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad 16-bit geometry w=%d h=%d stride=%d", w, h, stride);
+    if (h > 65535) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "at most 65535 rows");
+    if (w > ctx->max_w || h > ctx->max_h) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "frame %dx%d exceeds context maximum %dx%d", w, h, ctx->max_w, ctx->max_h);
+    if (tx < 1 || ty < 1) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", tx, ty);
+    return NV12EQ_OK;
+}
+
+int nv12eq_clahe16_device(nv12eq_ctx* ctx, const uint16_t* d_in, uint16_t* d_out, int n_planes, size_t plane_pitch, int width, int height,
+                          int stride, double clip_limit, int tiles_x, int tiles_y, void* cuda_stream) {
+    int rc = check_plane16(ctx, width, height, stride, tiles_x, tiles_y);
+    if (rc) return rc;
+    if (!d_in || !d_out || n_planes < 0 || n_planes > 65535 || (n_planes > 1 && plane_pitch < (size_t)stride * height))
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    DeviceGuard guard(ctx->device);
+    rc = launch_clahe16(ctx, ctx->dev_ws, d_in, d_out, n_planes, plane_pitch, width, height, stride, clip_limit, tiles_x, tiles_y,
+                        pick_stream(ctx, cuda_stream));
+    if (!rc) ctx->ctr.frames += (uint64_t)n_planes;
+    return rc;
+}
+
+// one 16-bit plane between host buffers with row strides in bytes; the device plane is packed
+static int plane16_host(nv12eq_ctx* ctx, const uint8_t* in, size_t in_stride, uint8_t* out, size_t out_stride, int w, int h, double clip,
+                        int tx, int ty) {
+    DeviceGuard guard(ctx->device);
+    Lane& L = ctx->lanes[0];
+    int rc = lane_wait(ctx, L);
+    if (rc) return rc;
+    const size_t plane = (size_t)w * h * sizeof(uint16_t);
+    if ((rc = dev_reserve(ctx, L.d_in, plane, false))) return rc;
+    if ((rc = dev_reserve(ctx, L.d_out, plane, false))) return rc;
+    CK(ctx, cudaMemcpy2DAsync(L.d_in.p, (size_t)w * 2, in, in_stride, (size_t)w * 2, (size_t)h, cudaMemcpyHostToDevice, L.stream));
+    rc = launch_clahe16(ctx, L.ws, reinterpret_cast<const uint16_t*>(L.d_in.p), reinterpret_cast<uint16_t*>(L.d_out.p), 1, (size_t)w * h, w, h,
+                        w, clip, tx, ty, L.stream);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpy2DAsync(out, out_stride, L.d_out.p, (size_t)w * 2, (size_t)w * 2, (size_t)h, cudaMemcpyDeviceToHost, L.stream));
+    ctx->ctr.bytes_in += plane; ctx->ctr.bytes_out += plane;
+    return NV12EQ_OK;
+}
+
+int nv12eq_clahe16(nv12eq_ctx* ctx, const uint16_t* in, uint16_t* out, int width, int height, int stride, double clip_limit, int tiles_x,
+                   int tiles_y) {
+    int rc = check_plane16(ctx, width, height, stride, tiles_x, tiles_y);
+    if (rc) return rc;
+    if (!in || !out) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "null plane pointer");
+    rc = plane16_host(ctx, reinterpret_cast<const uint8_t*>(in), (size_t)stride * 2, reinterpret_cast<uint8_t*>(out), (size_t)stride * 2, width,
+                      height, clip_limit, tiles_x, tiles_y);
+    if (rc) return rc;
+    CK(ctx, cudaStreamSynchronize(ctx->lanes[0].stream));
+    ctx->ctr.frames++;
+    return NV12EQ_OK;
+}
+
+int nv12eq_p010_clahe(nv12eq_ctx* ctx, const uint8_t* in, size_t in_size, uint8_t* out, size_t out_size, int width, int height, int stride,
+                      double clip_limit, int tiles_x, int tiles_y, int uv_mode) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (width <= 0 || height <= 0 || stride < 2 * width || (stride & 1)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad P010 geometry w=%d h=%d stride=%d", width, height, stride);
+    if (uv_mode < 0 || uv_mode > 2) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad uv_mode %d", uv_mode);
+    int rc = check_plane16(ctx, width, height, stride / 2, tiles_x, tiles_y);
+    if (rc) return rc;
+    if (!in || !out) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "null frame pointer");
+    const size_t need = (size_t)stride * (size_t)(height + height / 2);
+    if (in_size < need || out_size < need) return fail(ctx, NV12EQ_ERR_SHORT_BUFFER, "buffer %zu/%zu bytes < P010 frame %zu bytes", in_size, out_size, need);
+    rc = plane16_host(ctx, in, (size_t)stride, out, (size_t)stride, width, height, clip_limit, tiles_x, tiles_y);
+    if (rc) return rc;
+    // chroma on the host while the GPU works (neutral chroma of P010 = 512 << 6)
+    const size_t off = (size_t)stride * height;
+    for (int r = 0; r < height / 2 && uv_mode != UV_SKIP; ++r) {
+        uint8_t* d = out + off + (size_t)r * stride;
+        if (uv_mode == UV_COPY) { if (in != out) memcpy(d, in + off + (size_t)r * stride, (size_t)width * 2); }
+        else { uint16_t* d16 = reinterpret_cast<uint16_t*>(d); for (int c = 0; c < width; ++c) d16[c] = 0x8000; }
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->lanes[0].stream));
+    ctx->ctr.frames++;
+    return NV12EQ_OK;
 }
 
 // ---- BGR -> I420 adapter --------------------------------------------------------------------------------

@@ -241,6 +241,86 @@ ORACLE_API int oracle_clahe(const uint8_t* src, int sstride, uint8_t* dst, int d
     return 0;
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * CLAHE on CV_16UC1 (the P010 / 16-bit path OpenCV's CLAHE also accepts).
+ * Same algorithm as A.2 with histSize = 65536, lutScale = 65535.f / tileArea, clipLimit = clip * tileArea / 65536
+ * (>= 1 when clip > 0), 16-bit LUTs.  Verified bit-exact against cv2 4.13.0 (tests/golden/make_golden_ext.py).
+ * Strides are in ELEMENTS (uint16), not bytes.  Returns 0, -1 bad arguments, -2 out of memory.
+ * ---------------------------------------------------------------------------------------- */
+static inline uint16_t sat16(int v) { return (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v)); }
+
+ORACLE_API int oracle_clahe16(const uint16_t* src, int sstride, uint16_t* dst, int dstride, int W, int H,
+                              double clip, int tx, int ty) {
+    if (!src || !dst || W <= 0 || H <= 0 || tx < 1 || ty < 1) return -1;
+    int eW = W, eH = H;
+    if (W % tx != 0 || H % ty != 0) { eW = W + (tx - (W % tx)); eH = H + (ty - (H % ty)); }
+    const int tw = eW / tx, th = eH / ty, area = tw * th;
+    int clipLimit = 0;
+    if (clip > 0.0) { clipLimit = (int)(clip * area / 65536.0); if (clipLimit < 1) clipLimit = 1; }
+    const float lutScale = 65535.0f / (float)area;
+    uint16_t* luts = (uint16_t*)malloc((size_t)tx * ty * 65536 * sizeof(uint16_t));
+    int* h = (int*)malloc(sizeof(int) * 65536);
+    int* ind1 = (int*)malloc(sizeof(int) * W * 2);
+    float* xa = (float*)malloc(sizeof(float) * W * 2);
+    if (!luts || !h || !ind1 || !xa) { free(luts); free(h); free(ind1); free(xa); return -2; }
+    for (int tyi = 0; tyi < ty; ++tyi)
+        for (int txi = 0; txi < tx; ++txi) {
+            memset(h, 0, sizeof(int) * 65536);
+            for (int r = tyi * th; r < (tyi + 1) * th; ++r) {
+                const uint16_t* row = src + (size_t)reflect101(r, H) * sstride;
+                for (int c = txi * tw; c < (txi + 1) * tw; ++c) h[row[reflect101(c, W)]]++;
+            }
+            if (clipLimit > 0) {
+                long long clipped = 0;
+                for (int i = 0; i < 65536; ++i)
+                    if (h[i] > clipLimit) { clipped += h[i] - clipLimit; h[i] = clipLimit; }
+                int redistBatch = (int)(clipped / 65536);
+                int residual = (int)(clipped - (long long)redistBatch * 65536);
+                for (int i = 0; i < 65536; ++i) h[i] += redistBatch;
+                if (residual != 0) {
+                    int step = 65536 / residual; if (step < 1) step = 1;
+                    for (int i = 0; i < 65536 && residual > 0; i += step, residual--) h[i]++;
+                }
+            }
+            uint16_t* lut = luts + (size_t)(tyi * tx + txi) * 65536;
+            int sum = 0;
+            for (int i = 0; i < 65536; ++i) { sum += h[i]; lut[i] = sat16(rne((float)sum * lutScale)); }
+        }
+    int* ind2 = ind1 + W;
+    float* xa1 = xa + W;
+    const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+    for (int x = 0; x < W; ++x) {
+        float txf = (float)x * inv_tw - 0.5f;
+        int t1 = (int)floorf(txf), t2 = t1 + 1;
+        xa[x] = txf - (float)t1;
+        xa1[x] = 1.0f - xa[x];
+        if (t1 < 0) t1 = 0;
+        if (t2 > tx - 1) t2 = tx - 1;
+        ind1[x] = t1; ind2[x] = t2;
+    }
+    for (int y = 0; y < H; ++y) {
+        float tyf = (float)y * inv_th - 0.5f;
+        int t1 = (int)floorf(tyf), t2 = t1 + 1;
+        float ya = tyf - (float)t1, ya1 = 1.0f - ya;
+        if (t1 < 0) t1 = 0;
+        if (t2 > ty - 1) t2 = ty - 1;
+        const uint16_t* plane1 = luts + (size_t)t1 * tx * 65536;
+        const uint16_t* plane2 = luts + (size_t)t2 * tx * 65536;
+        const uint16_t* s = src + (size_t)y * sstride;
+        uint16_t* d = dst + (size_t)y * dstride;
+        for (int x = 0; x < W; ++x) {
+            int v = s[x];
+            float top = (float)plane1[(size_t)ind1[x] * 65536 + v] * xa1[x] + (float)plane1[(size_t)ind2[x] * 65536 + v] * xa[x];
+            float bot = (float)plane2[(size_t)ind1[x] * 65536 + v] * xa1[x] + (float)plane2[(size_t)ind2[x] * 65536 + v] * xa[x];
+            float res = top * ya1 + bot * ya;
+            d[x] = sat16(rne(res));
+        }
+    }
+    free(luts); free(h); free(ind1); free(xa);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------
  * NV12 frame-in / frame-out forms (the per-frame body of the reference worker,
  * nextimprovement.cpp:128-170 and clahevideo.cpp:158-201).

@@ -83,6 +83,9 @@ def lib() -> ctypes.CDLL:
         L.oracle_bgr2ycc.restype = None
         L.oracle_ycc2bgr.argtypes = [_u8p, c_int, _u8p, c_int, c_int, c_int, c_int]
         L.oracle_ycc2bgr.restype = None
+        u16p = ctypes.POINTER(ctypes.c_uint16)
+        L.oracle_clahe16.argtypes = [u16p, c_int, u16p, c_int, c_int, c_int, c_dbl, c_int, c_int]
+        L.oracle_clahe16.restype = c_int
         L.oracle_bgr2i420.argtypes = [_u8p, c_int, _u8p, c_int, c_int]
         L.oracle_bgr2i420.restype = c_int
         L.oracle_color_equalize.argtypes = [_u8p, _u8p, c_int, c_int, c_int, c_int, c_int, c_dbl, c_int, c_int]
@@ -155,6 +158,18 @@ def c_clahe(y: np.ndarray, clip=2.0, tx=8, ty=8) -> np.ndarray:
     rc = lib().oracle_clahe(_p(y), W, _p(out), W, W, H, float(clip), tx, ty)
     if rc:
         raise RuntimeError(f"oracle_clahe rc={rc}")
+    return out
+
+
+def c_clahe16(y: np.ndarray, clip=2.0, tx=8, ty=8) -> np.ndarray:
+    """CLAHE on a CV_16UC1 plane (OpenCV's 16-bit path: 65536 bins)."""
+    y = np.ascontiguousarray(y, dtype=np.uint16)
+    H, W = y.shape
+    out = np.empty_like(y)
+    u16p = ctypes.POINTER(ctypes.c_uint16)
+    rc = lib().oracle_clahe16(y.ctypes.data_as(u16p), W, out.ctypes.data_as(u16p), W, W, H, float(clip), tx, ty)
+    if rc:
+        raise RuntimeError(f"oracle_clahe16 rc={rc}")
     return out
 
 

@@ -144,3 +144,80 @@ def test_gpu_gstvideometa_layouts(nv, oracle):
         assert ctx.equalize_hist_meta(packed, W, H, bad, raw_status=True) == nv.ERR_INVALID_ARGUMENT
         far = nv.Layout(0, packed.size, W, W)
         assert ctx.equalize_hist_meta(packed, W, H, far, raw_status=True) == nv.ERR_SHORT_BUFFER
+
+
+# ------------------------------------------------------------------------------------------------------------
+# 16-bit CLAHE (CV_16UC1 / P010), SURVEY.md section 8f rank 3
+# ------------------------------------------------------------------------------------------------------------
+import sys  # noqa: E402
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from cases_ext import CLAHE16_PARAMS, plane16  # noqa: E402  (deterministic input generators, no cv2)
+
+
+def test_oracle_clahe16_matches_cv2_golden(oracle):
+    for rec in GOLD["clahe16"]:
+        if rec["W"] * rec["H"] > 1920 * 1080:
+            continue
+        y = plane16(rec["W"], rec["H"], rec["kind"], rec["seed"])
+        assert sha(y) == rec["in"]
+        for key, digest in rec["out"].items():
+            clip, tx, ty = key.split(":")
+            assert sha(oracle.c_clahe16(y, float(clip), int(tx), int(ty))) == digest, (rec["W"], rec["H"], key)
+    assert np.array_equal(oracle.c_clahe16(FIX["clahe16_34x18_in"], 2.0, 4, 3), FIX["clahe16_34x18_2.0_4_3"])
+
+
+@pytest.mark.gpu
+def test_gpu_clahe16_golden_and_p010_frames(nv, oracle):
+    with nv.Context(0, 3840, 2160, 1) as ctx:
+        for rec in GOLD["clahe16"]:
+            y = plane16(rec["W"], rec["H"], rec["kind"], rec["seed"])
+            for key, digest in rec["out"].items():
+                clip, tx, ty = key.split(":")
+                assert sha(ctx.clahe16(y, float(clip), (int(tx), int(ty)))) == digest, (rec["W"], rec["H"], key)
+        # strided plane (a view into a wider array)
+        wide = np.random.default_rng(3).integers(0, 65536, (50, 90), dtype=np.uint16)
+        view = wide[:, 5:5 + 70]
+        out = np.zeros_like(wide)
+        ctx.clahe16(view, 2.0, (4, 4), out=out[:, 5:5 + 70])
+        assert np.array_equal(out[:, 5:75], oracle.c_clahe16(np.ascontiguousarray(view), 2.0, 4, 4))
+        assert not out[:, :5].any() and not out[:, 75:].any()
+        # P010 frames: Y via the 16-bit CLAHE, chroma copied / neutral / untouched; padded rows stay untouched
+        W, H, S = 322, 200, 2 * 322 + 12
+        rng = np.random.default_rng(8)
+        y = plane16(W, H, "p010", 31)
+        uv = (rng.integers(0, 1024, (H // 2, W)).astype(np.uint16) << 6)
+        frame = np.full(S * (H + H // 2), 0xEE, np.uint8)
+        rows = frame.reshape(H + H // 2, S)
+        rows[:H, :2 * W] = y.view(np.uint8).reshape(H, 2 * W)
+        rows[H:, :2 * W] = uv.view(np.uint8).reshape(H // 2, 2 * W)
+        want_y = oracle.c_clahe16(y, 2.0, 8, 8)
+        for uv_mode in (nv.UV_COPY, nv.UV_GRAY128, nv.UV_SKIP):
+            out = ctx.p010_clahe(frame, W, H, 2.0, (8, 8), stride=S, uv_mode=uv_mode, out=np.full_like(frame, 0x11))
+            orow = out.reshape(H + H // 2, S)
+            assert np.array_equal(orow[:H, :2 * W].copy().view(np.uint16).reshape(H, W), want_y), uv_mode
+            got_uv = orow[H:, :2 * W].copy().view(np.uint16).reshape(H // 2, W)
+            if uv_mode == nv.UV_COPY:
+                assert np.array_equal(got_uv, uv)
+            elif uv_mode == nv.UV_GRAY128:
+                assert (got_uv == 0x8000).all()
+            else:
+                assert (orow[H:, :2 * W] == 0x11).all()
+            assert (orow[:, 2 * W:] == 0x11).all()
+        assert ctx.p010_clahe(frame[:100], W, H, raw_status=True, stride=S) == nv.ERR_SHORT_BUFFER
+        assert ctx.p010_clahe(frame, W, H, raw_status=True, stride=W) == nv.ERR_INVALID_ARGUMENT
+
+
+@pytest.mark.gpu
+def test_gpu_clahe16_device_batch(nv, oracle):
+    import torch
+    W, H, n = 640, 360, 20          # 20 planes x 64 tiles: two workspace passes (16 + 4)
+    planes = np.stack([plane16(W, H, "p010", 40 + k) for k in range(n)])
+    with nv.Context(0, W, H, 1) as ctx:
+        d_in = torch.from_numpy(planes.view(np.int16)).cuda()
+        d_out = torch.zeros_like(d_in)
+        ctx.clahe16_device(d_in, d_out, n, W * H, W, H, 2.0, (8, 8), stream=torch.cuda.current_stream())
+        ctx.clahe16_device(d_in, d_out, n, W * H, W, H, 2.0, (8, 8), stream=torch.cuda.current_stream())  # workspace is self-cleaning
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(np.uint16)
+        for k in (0, 7, 15, 16, 19):
+            assert np.array_equal(got[k], oracle.c_clahe16(planes[k], 2.0, 8, 8)), k
