@@ -4,32 +4,34 @@
 // with the NV12 rebuild around it (clahevideo.cpp:200-201).
 //
 // Stages (all inside one kernel, scheduled with the same ticket-lag scheme as equalize.cuh):
-//   tile item  (frame g, tile t): 256-bin histogram of the tile in smem hist[256][32] (conflict-free lane columns),
-//              then one warp clips at clipLimit, redistributes the excess exactly as OpenCV does (redistBatch to
+//   tile item  (frame g, tile t): tile rows staged through a per-thread cp.async ring, 256-bin histogram of the tile in smem
+//              hist[256][32] (conflict-free lane columns), then one warp clips at clipLimit, redistributes the excess exactly as OpenCV does (redistBatch to
 //              every bin, then +1 to every residualStep-th bin while residual lasts), scans, and writes the tile's
 //              256-byte LUT (cvRound(sum * lutScale), fp32, round-half-even).  The padding path
 //              (copyMakeBorder BORDER_REFLECT_101 when the grid does not divide the image) is an index reflection
 //              in the tile reader; the padded image is never materialised.
 //   cell item  (frame f = g - lag, interpolation cell (i, j)): a cell is a rectangle of pixels that blend the same
-//              four tile LUTs.  The CTA packs those four LUTs into table[v][32] = {bf16 L11 | L21, bf16 L12 | L22}
-//              (exact: 0..255 fit bf16 and widening bf16->fp32 is a shift; one 8-byte replica per lane makes the
-//              gather conflict-free), then every pixel does ONE shared gather and OpenCV's blend op for op in
+//              four tile LUTs.  The CTA packs those four LUTs into table[v][reps] = {bf16 L11 | L21, bf16 L12 | L22}
+//              (exact: 0..255 fit bf16 and widening bf16->fp32 is a shift; 16 or 32 8-byte replicas make a half-warp
+//              gather conflict-free), pixel rows arrive through a per-thread cp.async ring (16 or 8 pixels per thread
+//              and row), then every pixel does ONE shared gather and OpenCV's blend op for op in
 //              unfused fp32, the top and bottom row of the 2x2 LUT neighbourhood side by side in packed fp32:
 //                  (top, bot) = (L11, L21)*xa1 + (L12, L22)*xa        FMUL2, FMUL2, FADD2
 //                  res        = top*ya1 + bot*ya                      FMUL2, FADD
 //                  dst        = saturate(cvRound(res))                FADD2 with 1.5*2^23 on a pixel pair, PRMT
-//              Entries are 256 bytes apart, so ONE PRMT turns a pixel byte into the shared address of its entry
-//              (byte 1 = pixel value, byte 0 = lane*8); the histogram of tile items uses the same 256-byte rows.
+//              Table rows are 128 bytes apart by default (PRMT + multiply-add per address); the 256-byte variant turns a
+//              pixel byte into the row offset with ONE PRMT (byte 1 = pixel value, byte 0 = lane offset) but needs a 64 KB
+//              table, i.e. fewer CTAs per SM, and measured slower (profiles/r01_clahe_notes.md).
 //   uv item    (frame f, chunk): chroma passthrough / 128 fill.
 //
 // Roofline: HBM, 3*W*H algorithmic bytes per frame (tile LUTs are 16 KB per frame).  Secondary limiters: shared
-// atomics (tile items) and instruction issue (cell items: ~18 instructions per pixel).
+// atomics (tile items) and instruction issue (cell items: ~15 instructions per pixel).
 #pragma once
 #include "common.cuh"
 
 // Dynamic shared memory of clahe_kernel, declared at global scope so that its PTX name is unmangled: the kernel takes
-// its address with `mov.u32 r, nv12eq_smem_rows` -- a link-time constant that ptxas folds into the immediate offset of
-// every LDS / ATOMS / LDGSTS ([R + imm]), instead of carrying a base register and an add per access.
+// its address with `mov.u32 r, nv12eq_smem_rows`, a plain shared-window offset (cvta would add the CTA's cluster-window
+// bits), which keeps ring and table addresses simple register + immediate forms.
 extern __shared__ __align__(256) uint32_t nv12eq_smem_rows[];
 
 namespace nv12eq {
@@ -37,10 +39,11 @@ namespace nv12eq {
 constexpr int kMaxCells = 4096;  // per axis (tiles + 1); plenty
 constexpr int kMaxCellRows = 512;               // rows per interpolation cell (host cuts longer runs)
 // CTA shape of clahe_kernel (compile-time; the Makefile's EXTRA can override for experiments):
-//   256 threads x 4 CTAs/SM with 128-byte table rows (32 KB table) -- the default: four independent items per SM fill the
-//       bubbles of the per-item phases (table build, LUT warp, barriers); measured 8.1 us vs 9.1 us per 4K frame and
-//       2.6 us vs 3.6 us per 1080p frame against
+//   256 threads x 4 (or 3) CTAs/SM with 128-byte table rows (32 KB table) -- the default: several independent items per SM
+//       fill the bubbles of the per-item phases (table build, LUT warp, barriers); measured 8.1 us vs 9.1 us per 4K frame
+//       and 2.6 us vs 3.6 us per 1080p frame against
 //   512 threads x 2 CTAs/SM with 256-byte table rows (one-PRMT addressing, 64 KB table).
+//   The host launches the <kClaheCtas - 1> instantiation (more registers per thread) for tiles of 64 K pixels and more.
 #ifndef NV12EQ_CLAHE_THREADS
 #define NV12EQ_CLAHE_THREADS 256
 #endif
