@@ -27,6 +27,7 @@ namespace nv12eq {
 constexpr int kEqCtas = NV12EQ_EQ_CTAS;  // CTAs per SM equalize_kernel is built for
 constexpr int kThreads = NV12EQ_EQ_THREADS;  // threads per CTA of equalize_kernel (512 x 2 CTAs/SM: 32 warps, 64 registers/thread)
 constexpr int kWarps = kThreads / 32;
+static_assert(kThreads == 256 || kThreads == 512 || kThreads == 1024, "lane-table helpers divide 2048 vectors / 256 values evenly over the CTA");
 constexpr int kLaneTableWords = 256 * 32; // one [256][32] uint32 table
 constexpr int kLaneTableBytes = kLaneTableWords * 4;
 
