@@ -173,16 +173,19 @@ def calibrate_cpu_frames(args, W, H, target_s, passes):
     cores = os.cpu_count() or 1
     nv12 = O.c_synth_nv12(W, H, 2026, 0)
     out = np.empty_like(nv12)
-    t0 = time.perf_counter()
-    if O.have_cv2():
-        import cv2
-        cv2.setNumThreads(1)
-        if args.op == "equalize":
-            O.cv2_nv12_equalize_hist(nv12, W, H, out)
+    def one():
+        if O.have_cv2():
+            import cv2
+            cv2.setNumThreads(1)
+            if args.op == "equalize":
+                O.cv2_nv12_equalize_hist(nv12, W, H, out)
+            else:
+                O.cv2_nv12_clahe(nv12, W, H, out, clip=args.clip, tx=args.tiles, ty=args.tiles)
         else:
-            O.cv2_nv12_clahe(nv12, W, H, out, clip=args.clip, tx=args.tiles, ty=args.tiles)
-    else:
-        O.c_nv12_batch(args.op, nv12[None], W, H, clip=args.clip, tx=args.tiles, ty=args.tiles, threads=1)
+            O.c_nv12_batch(args.op, nv12[None], W, H, clip=args.clip, tx=args.tiles, ty=args.tiles, threads=1)
+    one()                      # first call: imports, page faults, thread pools
+    t0 = time.perf_counter()
+    one()
     per_frame = max(time.perf_counter() - t0, 1e-4)
     n = int(target_s / passes / per_frame * min(cores, 16))
     n = max(min(cores, 128), min(n, 128))
