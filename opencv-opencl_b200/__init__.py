@@ -73,13 +73,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))] + [HEADER_PATH]
     if os.environ.get("NV12EQ_LIB"):
         return LIB_PATH  # an explicitly selected experimental build is used as is
-    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
-    if force or stale:
-        out = subprocess.run(["make", "-C", csrc] + (["-B"] if force else []), capture_output=True, text=True)
-        if verbose or out.returncode:
-            print(out.stdout + out.stderr)
-        if out.returncode:
-            raise RuntimeError("building libnv12eq.so failed (see output above)")
+    def stale():
+        return (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale():
+        # several ranks of one torchrun job may get here at once: one builds, the others wait and then find it fresh
+        import fcntl
+        with open(os.path.join(csrc, ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or stale():
+                    out = subprocess.run(["make", "-C", csrc] + (["-B"] if force else []), capture_output=True, text=True)
+                    if verbose or out.returncode:
+                        print(out.stdout + out.stderr)
+                    if out.returncode:
+                        raise RuntimeError("building libnv12eq.so failed (see output above)")
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
