@@ -168,14 +168,37 @@ __device__ __forceinline__ SpanSplit split_span(const void* p, size_t n) {
 }
 
 // Software-pipelined walk over nvec 32-byte vectors, thread `tid` of `nthr` taking vectors tid, tid+nthr, ...
-// Two register slots per thread: a slot is refilled (load of the vector two steps ahead) as soon as it has been
-// consumed, so a thread always has one or two 32-byte loads in flight while it works: 32-64 KB per SM at 1024
-// threads, which covers HBM latency at the per-SM share of the bandwidth.
+// Three register slots per thread (NV12EQ_PIPE_SLOTS): a slot is refilled (load of the vector three steps ahead) as soon
+// as it has been consumed, so a thread always has two or three 32-byte loads in flight while it works: 64-96 KB per SM
+// at 1024 threads, which covers the loaded HBM latency at the per-SM share of the bandwidth (two slots: 1 % slower).
+#ifndef NV12EQ_PIPE_SLOTS
+#define NV12EQ_PIPE_SLOTS 3
+#endif
 template <class Load, class Use>
 __device__ __forceinline__ void pipelined_vectors(uint32_t nvec, int tid, int nthr, Load load, Use use) {
     const uint32_t K = nvec > (uint32_t)tid ? (nvec - tid + nthr - 1) / nthr : 0u;  // vectors of this thread
     const uint32_t step = (uint32_t)nthr;
     uint32_t i = tid;
+#if NV12EQ_PIPE_SLOTS == 3
+    V8 a, b, c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.r[j] = b.r[j] = c.r[j] = 0;
+    if (K > 0) a = load(i);
+    if (K > 1) b = load(i + step);
+    if (K > 2) c = load(i + 2 * step);
+    uint32_t k = 0;
+    for (; k + 3 <= K; k += 3) {
+        use(i, a);
+        if (k + 3 < K) a = load(i + 3 * step);
+        use(i + step, b);
+        if (k + 4 < K) b = load(i + 4 * step);
+        use(i + 2 * step, c);
+        if (k + 5 < K) c = load(i + 5 * step);
+        i += 3 * step;
+    }
+    if (k < K) use(i, a);
+    if (k + 1 < K) use(i + step, b);
+#else
     V8 a, b;
 #pragma unroll
     for (int j = 0; j < 8; ++j) a.r[j] = b.r[j] = 0;
@@ -190,6 +213,7 @@ __device__ __forceinline__ void pipelined_vectors(uint32_t nvec, int tid, int nt
         i += 2 * step;
     }
     if (k < K) use(i, a);
+#endif
 }
 
 // A lane-private table lives at 32-bit shared address `lane_base` (= table base + lane*4); the entry of value v
