@@ -265,47 +265,60 @@ __device__ __forceinline__ void pin_register(float& v) { asm volatile("" : "+f"(
 // (tr == 0, the most rows) draws the next ticket at the start of the last round, which hides the atomic's round trip.
 // G = 16 halves the per-row overhead (ring, pointers, y weights, loop) per pixel; it needs 32 registers of x weights.
 template <int G>
-__device__ __forceinline__ void clahe_cell_rows(TicketQueue& q, const uint8_t* sp, uint8_t* dp, size_t rstep, int nrows, int xg, float inv_tw,
-                                                uint32_t ring0, uint32_t yw_addr, uint32_t yw_step, uint32_t lane8) {
-    constexpr int D = (G == 16) ? kRingDepth / 2 : kRingDepth;   // same ring bytes either way
-    constexpr uint32_t kSlot = kCT * G;
+struct CellRows {
+    static constexpr int D = (G == 16) ? kRingDepth / 2 : kRingDepth;   // same ring bytes either way
+    static constexpr uint32_t kSlot = kCT * G;
     float xa[G], xa1[G];
-#pragma unroll
-    for (int k = 0; k < G; ++k) axis_weight(xg + k, inv_tw, xa[k], xa1[k]);
-    auto issue = [&](uint32_t slot, const uint8_t* g) {
+    const uint8_t* spn;
+    uint8_t* dp;
+    size_t rstep;
+    uint32_t ring0, yw_addr, yw_step;
+    int nrows;
+
+    __device__ __forceinline__ void issue(uint32_t slot, const uint8_t* g) const {
         if (G == 16) cp_async16(ring0 + slot * kSlot, g); else cp_async8(ring0 + slot * kSlot, g);
-    };
-#pragma unroll
-    for (int j = 0; j < D - 1; ++j) {
-        if (j < nrows) issue((uint32_t)j, sp + (size_t)j * rstep);
-        cp_async_commit();
     }
-    const uint8_t* spn = sp + (size_t)(D - 1) * rstep;
-#pragma unroll 1
-    for (int i0 = 0; i0 < nrows; i0 += D) {
-        if (i0 + D >= nrows) q.prefetch();
+    // Everything that does not depend on the tile LUTs: x weights and the first D-1 rows of the ring.  Called BEFORE the
+    // dependency wait and the table build, so the pixel loads are in flight while the CTA waits for / packs the LUTs.
+    __device__ __forceinline__ void start(const uint8_t* sp, uint8_t* dp_, size_t rstep_, int nrows_, int xg, float inv_tw, uint32_t ring0_,
+                                          uint32_t yw_addr_, uint32_t yw_step_) {
+        dp = dp_; rstep = rstep_; nrows = nrows_; ring0 = ring0_; yw_addr = yw_addr_; yw_step = yw_step_;
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const int i = i0 + j;
-            if (i < nrows) {
-                if (i + D - 1 < nrows) issue((uint32_t)((j + D - 1) % D), spn);
-                cp_async_commit();
-                cp_async_wait<D - 1>();
-                const uint64_t yw = lds_b64(yw_addr);
-                if (G == 16) {
-                    const int4 px = lds_s4(ring0 + (uint32_t)j * kSlot);
-                    const uint2 o0 = clahe_blend_8(make_uint2((uint32_t)px.x, (uint32_t)px.y), lane8, xa, xa1, yw);
-                    const uint2 o1 = clahe_blend_8(make_uint2((uint32_t)px.z, (uint32_t)px.w), lane8, xa + 8 * (G / 16), xa1 + 8 * (G / 16), yw);
-                    __stcs(reinterpret_cast<uint4*>(dp), make_uint4(o0.x, o0.y, o1.x, o1.y));
-                } else {
-                    const uint2 px = lds_u64(ring0 + (uint32_t)j * kSlot);
-                    __stcs(reinterpret_cast<uint2*>(dp), clahe_blend_8(px, lane8, xa, xa1, yw));
+        for (int k = 0; k < G; ++k) axis_weight(xg + k, inv_tw, xa[k], xa1[k]);
+#pragma unroll
+        for (int j = 0; j < D - 1; ++j) {
+            if (j < nrows) issue((uint32_t)j, sp + (size_t)j * rstep);
+            cp_async_commit();
+        }
+        spn = sp + (size_t)(D - 1) * rstep;
+    }
+    __device__ __forceinline__ void run(TicketQueue& q, uint32_t lane8) {
+#pragma unroll 1
+        for (int i0 = 0; i0 < nrows; i0 += D) {
+            if (i0 + D >= nrows) q.prefetch();
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const int i = i0 + j;
+                if (i < nrows) {
+                    if (i + D - 1 < nrows) issue((uint32_t)((j + D - 1) % D), spn);
+                    cp_async_commit();
+                    cp_async_wait<D - 1>();
+                    const uint64_t yw = lds_b64(yw_addr);
+                    if (G == 16) {
+                        const int4 px = lds_s4(ring0 + (uint32_t)j * kSlot);
+                        const uint2 o0 = clahe_blend_8(make_uint2((uint32_t)px.x, (uint32_t)px.y), lane8, xa, xa1, yw);
+                        const uint2 o1 = clahe_blend_8(make_uint2((uint32_t)px.z, (uint32_t)px.w), lane8, xa + 8 * (G / 16), xa1 + 8 * (G / 16), yw);
+                        __stcs(reinterpret_cast<uint4*>(dp), make_uint4(o0.x, o0.y, o1.x, o1.y));
+                    } else {
+                        const uint2 px = lds_u64(ring0 + (uint32_t)j * kSlot);
+                        __stcs(reinterpret_cast<uint2*>(dp), clahe_blend_8(px, lane8, xa, xa1, yw));
+                    }
+                    spn += rstep; dp += rstep; yw_addr += yw_step;
                 }
-                spn += rstep; dp += rstep; yw_addr += yw_step;
             }
         }
     }
-}
+};
 
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams p) {
@@ -345,41 +358,42 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 const uint8_t* y = p.in + (unsigned long long)g * p.pitch;
                 const int tyi = r / p.tx, txi = r - tyi * p.tx;
                 const int x0 = txi * p.tw, y0 = tyi * p.th;
+                const uint64_t keep = l2_policy_evict_last();
+                const bool vec_ok = !(p.debug_skip & 1) && !p.padded && (p.tw & 15) == 0 && (p.stride & 15) == 0 &&
+                                    (((uintptr_t)y + (uintptr_t)x0) & 15) == 0 && (p.tw >> 4) <= kCT;
+                // threads form a (rows_per_pass x vectors_per_row) grid over the tile.  Every thread keeps
+                // kTileDepth-1 of its 16-byte row pieces in flight through a private cp.async ring; the first ones are issued
+                // before the table is zeroed so that their latency overlaps the set-up of the item.
+                const int vpr = vec_ok ? (p.tw >> 4) : 1;
+                const int rpp = kCT / vpr;
+                const int tr = tid / vpr, tc = tid - tr * vpr;
+                const int nrows = (vec_ok && tr < rpp && tr < p.th) ? (p.th - tr + rpp - 1) / rpp : 0;
+                const uint8_t* ptr = y + (size_t)(y0 + tr) * p.stride + x0 + tc * 16;
+                const size_t rstep = (size_t)rpp * p.stride;
+                const uint32_t ring0 = rbase + (uint32_t)tid * 16u;
+                constexpr uint32_t kSlot = kCT * 16u, kRingMask = kTileDepth * kSlot - 1u;
+                if (vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < kTileDepth - 1; ++j) {
+                        if (j < nrows) cp_async16(ring0 + (uint32_t)j * kSlot, ptr + (size_t)j * rstep);
+                        cp_async_commit();
+                    }
+                }
                 hist256_zero(smem_rows);
                 __syncthreads();
-                const uint64_t keep = l2_policy_evict_last();
-                const bool vec_ok = !p.padded && (p.tw & 15) == 0 && (p.stride & 15) == 0 &&
-                                    (((uintptr_t)y + (uintptr_t)x0) & 15) == 0 && (p.tw >> 4) <= kCT;
                 if (p.debug_skip & 1) {
                 } else if (vec_ok) {
-                    // threads form a (rows_per_pass x vectors_per_row) grid over the tile.  Every thread keeps
-                    // kTileDepth-1 of its 16-byte row pieces in flight through a private cp.async ring (64 KB per SM).
-                    const int vpr = p.tw >> 4;
-                    const int rpp = kCT / vpr;
-                    const int tr = tid / vpr, tc = tid - tr * vpr;
-                    if (tr < rpp && tr < p.th) {
-                        const uint8_t* ptr = y + (size_t)(y0 + tr) * p.stride + x0 + tc * 16;
-                        const size_t rstep = (size_t)rpp * p.stride;
-                        const int nrows = (p.th - tr + rpp - 1) / rpp;
-                        const uint32_t ring0 = rbase + (uint32_t)tid * 16u;
-                        constexpr uint32_t kSlot = kCT * 16u, kRingMask = kTileDepth * kSlot - 1u;
-#pragma unroll
-                        for (int j = 0; j < kTileDepth - 1; ++j) {
-                            if (j < nrows) cp_async16(ring0 + (uint32_t)j * kSlot, ptr + (size_t)j * rstep);
-                            cp_async_commit();
-                        }
-                        const uint8_t* pn = ptr + (size_t)(kTileDepth - 1) * rstep;
-                        uint32_t rd = 0u, wr = (uint32_t)(kTileDepth - 1) * kSlot;
+                    const uint8_t* pn = ptr + (size_t)(kTileDepth - 1) * rstep;
+                    uint32_t rd = 0u, wr = (uint32_t)(kTileDepth - 1) * kSlot;
 #pragma unroll 1
-                        for (int i = 0; i < nrows; ++i) {
-                            if (i + kTileDepth - 1 < nrows) cp_async16(ring0 + wr, pn);
-                            cp_async_commit();
-                            cp_async_wait<kTileDepth - 1>();
-                            hist256_vec(lds_s4(ring0 + rd), tbase, lane4);
-                            pn += rstep;
-                            wr = rd;
-                            rd = (rd + kSlot) & kRingMask;
-                        }
+                    for (int i = 0; i < nrows; ++i) {
+                        if (i + kTileDepth - 1 < nrows) cp_async16(ring0 + wr, pn);
+                        cp_async_commit();
+                        cp_async_wait<kTileDepth - 1>();
+                        hist256_vec(lds_s4(ring0 + rd), tbase, lane4);
+                        pn += rstep;
+                        wr = rd;
+                        rd = (rd + kSlot) & kRingMask;
                     }
                 } else {
                     // general path: one warp per tile row, byte spans inside the image, reflected reads outside
@@ -411,71 +425,85 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 const int cy = ci / p.nxc, cx = ci - cy * p.nxc;
                 const int4 xc = p.xcells[cx], yc = p.ycells[cy];
                 const int cw = xc.y - xc.x, ch = yc.y - yc.x;  // cell size in pixels (ch <= kMaxCellRows)
-                // y weights of the cell's rows (does not depend on the tile LUTs: done before the dependency wait)
-                for (int i = tid; i < ch; i += kCT) {
-                    float ya, ya1;
-                    axis_weight(yc.x + i, p.inv_th, ya, ya1);
-                    s_yw[i] = make_float2(ya1, ya);
-                }
-                if (tid == 0) {
-                    bool ok = true;
-                    if (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
-                        const long long t0 = clock64();
-                        unsigned ns = 64;
-                        while (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
-                            __nanosleep(ns);
-                            if (ns < 2048) ns <<= 1;
-                            if (clock64() - t0 > kSpinCycles) { ok = false; break; }
-                        }
-                    }
-                    if (!ok) atomicExch(p.status, 1u);
-                    s_flag = ok;
-                }
-                __syncthreads();
-                if (!s_flag) break;
-                tr_.mark(item, 1);
-                if (!(p.debug_skip & 16))
-                // pack the four LUTs: row v = 32 lane replicas of {bf16 L11 | L21 << 16, bf16 L12 | L22 << 16}
-                {
-                    constexpr int kShare = kCT / 256, kPer = kCellReps / kShare;
-                    const uint8_t* L = p.luts + (size_t)f * T * 256;
-                    const int v = tid & 255, part = tid >> 8;
-                    const uint32_t l11 = __ldcg(L + (size_t)(yc.z * p.tx + xc.z) * 256 + v);
-                    const uint32_t l12 = __ldcg(L + (size_t)(yc.z * p.tx + xc.w) * 256 + v);
-                    const uint32_t l21 = __ldcg(L + (size_t)(yc.w * p.tx + xc.z) * 256 + v);
-                    const uint32_t l22 = __ldcg(L + (size_t)(yc.w * p.tx + xc.w) * 256 + v);
-                    uint2 e;
-                    e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l21) & 0xffff0000u);
-                    e.y = (__float_as_uint((float)l12) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
-                    uint2* row = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(smem_rows) + v * kRowBytes);
-#pragma unroll
-                    for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & (kCellReps - 1)] = e;
-                }
-                __syncthreads();
+                // Geometry of the fast path: full groups of G = 16 (or 8) pixels, one 16- (8-) byte load / store per thread and
+                // row.  Columns left over when the cell width is not a multiple of G (and everything when alignment does not
+                // allow vector accesses) take the pixel-at-a-time path below.
                 const uint32_t ywbase = smem_u32(s_yw);
-                // Fast path: full groups of G = 16 (or 8) pixels, one 16- (8-) byte load / store per thread and row.  Columns
-                // left over when the cell width is not a multiple of G (and everything when alignment does not allow vector
-                // accesses) take the pixel-at-a-time path below.
                 const uintptr_t align_or = (uintptr_t)src | (uintptr_t)dst | (uintptr_t)p.stride | (uintptr_t)xc.x;
                 const bool fast16 = ((align_or & 15) == 0) && (cw & 15) == 0 && (cw >> 4) >= 1 && (cw >> 4) <= kCT;
                 const bool fast8 = !fast16 && ((align_or & 7) == 0) && (cw >> 3) >= 1 && (cw >> 3) <= kCT;
                 const int G = fast16 ? 16 : 8;
-                const int gpr = fast16 ? (cw >> 4) : (fast8 ? (cw >> 3) : 0);   // G-pixel groups per row
+                const int gpr = (p.debug_skip & 2) ? 0 : (fast16 ? (cw >> 4) : (fast8 ? (cw >> 3) : 0));   // G-pixel groups per row
                 const int xslow = xc.x + gpr * G;                               // first column of the pixel-at-a-time path
-                if (gpr > 0 && !(p.debug_skip & 2)) {
-                    const int rpp = kCT / gpr;
-                    const int tr = tid / gpr, tc = tid - tr * gpr;
-                    const int xg = xc.x + tc * G;
-                    if (tr < rpp && tr < ch) {
-                        const size_t rstep = (size_t)rpp * p.stride;
-                        const int nrows = (ch - tr + rpp - 1) / rpp;  // rows of this thread: tr, tr + rpp, ...
-                        const uint8_t* sp = src + (size_t)(yc.x + tr) * p.stride + xg;
-                        uint8_t* dp = dst + (size_t)(yc.x + tr) * p.stride + xg;
-                        const uint32_t yw_addr = ywbase + (uint32_t)tr * 8u, yw_step = (uint32_t)rpp * 8u;
-                        if (fast16) clahe_cell_rows<16>(q, sp, dp, rstep, nrows, xg, p.inv_tw, rbase + (uint32_t)tid * 16u, yw_addr, yw_step, lane8);
-                        else clahe_cell_rows<8>(q, sp, dp, rstep, nrows, xg, p.inv_tw, rbase + (uint32_t)tid * 8u, yw_addr, yw_step, lane8);
+                const int rpp = gpr ? kCT / gpr : 1;
+                const int tr = gpr ? tid / gpr : 0, tc = tid - tr * gpr;
+                const bool active = gpr > 0 && tr < rpp && tr < ch;
+                const int xg = xc.x + tc * G;
+                const size_t rstep = (size_t)rpp * p.stride;
+                const int nrows = active ? (ch - tr + rpp - 1) / rpp : 0;   // rows of this thread: tr, tr + rpp, ...
+                const uint8_t* sp = src + (size_t)(yc.x + tr) * p.stride + xg;
+                uint8_t* dp = dst + (size_t)(yc.x + tr) * p.stride + xg;
+                const uint32_t yw_addr = ywbase + (uint32_t)tr * 8u, yw_step = (uint32_t)rpp * 8u;
+
+                // dependency wait + table build; everything the row loop needs that does not depend on the LUTs has been
+                // started by then (CellRows::start), so pixel loads overlap the wait and the LUT loads
+                auto wait_and_build_table = [&]() -> bool {
+                    // y weights of the cell's rows
+                    for (int i = tid; i < ch; i += kCT) {
+                        float ya, ya1;
+                        axis_weight(yc.x + i, p.inv_th, ya, ya1);
+                        s_yw[i] = make_float2(ya1, ya);
                     }
+                    if (tid == 0) {
+                        bool ok = true;
+                        if (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
+                            const long long t0 = clock64();
+                            unsigned ns = 64;
+                            while (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
+                                __nanosleep(ns);
+                                if (ns < 2048) ns <<= 1;
+                                if (clock64() - t0 > kSpinCycles) { ok = false; break; }
+                            }
+                        }
+                        if (!ok) atomicExch(p.status, 1u);
+                        s_flag = ok;
+                    }
+                    __syncthreads();
+                    if (!s_flag) return false;
+                    tr_.mark(item, 1);
+                    if (!(p.debug_skip & 16))
+                    // pack the four LUTs: row v = replicas of {bf16 L11 | L21 << 16, bf16 L12 | L22 << 16}
+                    {
+                        constexpr int kShare = kCT / 256, kPer = kCellReps / kShare;
+                        const uint8_t* L = p.luts + (size_t)f * T * 256;
+                        const int v = tid & 255, part = tid >> 8;
+                        const uint32_t l11 = __ldcg(L + (size_t)(yc.z * p.tx + xc.z) * 256 + v);
+                        const uint32_t l12 = __ldcg(L + (size_t)(yc.z * p.tx + xc.w) * 256 + v);
+                        const uint32_t l21 = __ldcg(L + (size_t)(yc.w * p.tx + xc.z) * 256 + v);
+                        const uint32_t l22 = __ldcg(L + (size_t)(yc.w * p.tx + xc.w) * 256 + v);
+                        uint2 e;
+                        e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l21) & 0xffff0000u);
+                        e.y = (__float_as_uint((float)l12) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
+                        uint2* row = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(smem_rows) + v * kRowBytes);
+#pragma unroll
+                        for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & (kCellReps - 1)] = e;
+                    }
+                    __syncthreads();
+                    return true;
+                };
+                bool ok;
+                if (fast16) {
+                    CellRows<16> rows;
+                    rows.start(sp, dp, rstep, nrows, xg, p.inv_tw, rbase + (uint32_t)tid * 16u, yw_addr, yw_step);
+                    ok = wait_and_build_table();
+                    if (ok) rows.run(q, lane8);
+                } else {
+                    CellRows<8> rows;
+                    rows.start(sp, dp, rstep, nrows, xg, p.inv_tw, rbase + (uint32_t)tid * 8u, yw_addr, yw_step);
+                    ok = wait_and_build_table();
+                    if (ok) rows.run(q, lane8);
                 }
+                if (!ok) break;
                 if (xslow < xc.y && !(p.debug_skip & 2)) {
                     // pixel-at-a-time path
                     const int sw = xc.y - xslow;
