@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 const uint8_t* ptr = y + (size_t)(y0 + tr) * p.stride + x0 + tc * 16;
                 const size_t rstep = (size_t)rpp * p.stride;
                 const uint32_t ring0 = rbase + (uint32_t)tid * 16u;
-                constexpr uint32_t kSlot = kCT * 16u, kRingMask = kTileDepth * kSlot - 1u;
+                constexpr uint32_t kSlot = kCT * 16u;
                 if (vec_ok) {
 #pragma unroll
                     for (int j = 0; j < kTileDepth - 1; ++j) {
@@ -384,16 +384,20 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 if (p.debug_skip & 1) {
                 } else if (vec_ok) {
                     const uint8_t* pn = ptr + (size_t)(kTileDepth - 1) * rstep;
-                    uint32_t rd = 0u, wr = (uint32_t)(kTileDepth - 1) * kSlot;
+                    // unrolled by the ring depth: every slot is a compile-time offset
 #pragma unroll 1
-                    for (int i = 0; i < nrows; ++i) {
-                        if (i + kTileDepth - 1 < nrows) cp_async16(ring0 + wr, pn);
-                        cp_async_commit();
-                        cp_async_wait<kTileDepth - 1>();
-                        hist256_vec(lds_s4(ring0 + rd), tbase, lane4);
-                        pn += rstep;
-                        wr = rd;
-                        rd = (rd + kSlot) & kRingMask;
+                    for (int i0 = 0; i0 < nrows; i0 += kTileDepth) {
+#pragma unroll
+                        for (int j = 0; j < kTileDepth; ++j) {
+                            const int i = i0 + j;
+                            if (i < nrows) {
+                                if (i + kTileDepth - 1 < nrows) cp_async16(ring0 + (uint32_t)((j + kTileDepth - 1) % kTileDepth) * kSlot, pn);
+                                cp_async_commit();
+                                cp_async_wait<kTileDepth - 1>();
+                                hist256_vec(lds_s4(ring0 + (uint32_t)j * kSlot), tbase, lane4);
+                                pn += rstep;
+                            }
+                        }
                     }
                 } else {
                     // general path: one warp per tile row, byte spans inside the image, reflected reads outside
