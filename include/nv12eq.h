@@ -186,6 +186,10 @@ int nv12eq_color_equalize(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_o
                           int color_mode);
 int nv12eq_color_clahe(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_out, int width, int height, int stride,
                        int color_mode, double clip_limit, int tiles_x, int tiles_y);
+/* Host batch: n_frames packed BGR frames, frame k at in + k*frame_pitch (frame_pitch >= stride*height); pipelined over the
+ * context's slots like the NV12 batch forms. */
+int nv12eq_color_equalize_batch(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_out, int n_frames, size_t frame_pitch, int width,
+                                int height, int stride, int color_mode);
 int nv12eq_color_equalize_device(nv12eq_ctx* ctx, const uint8_t* d_bgr_in, uint8_t* d_bgr_out, int n_frames,
                                  size_t frame_pitch, int width, int height, int stride, int color_mode,
                                  void* cuda_stream);

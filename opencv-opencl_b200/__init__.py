@@ -117,6 +117,7 @@ _SIGNATURES = {
     "nv12eq_hist_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "nv12eq_equalize_apply_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_vp, ctypes.c_int64, _c_vp]),
     "nv12eq_color_equalize": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int]),
+    "nv12eq_color_equalize_batch": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int]),
     "nv12eq_color_clahe": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int]),
     "nv12eq_color_equalize_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "nv12eq_color_clahe_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_vp]),
@@ -409,6 +410,14 @@ class Context:
         h, w, _ = bgr.shape
         out = np.empty_like(bgr) if out is None else out
         self._check(self._lib.nv12eq_color_equalize(self._h, _ptr(bgr), _ptr(out), w, h, bgr.strides[0], color_mode))
+        return out
+
+    def color_equalize_batch(self, frames: np.ndarray, color_mode: int = COLOR_YUV, out=None) -> np.ndarray:
+        """(n, H, W, 3) uint8 BGR frames through the colour path, pipelined over the context's slots."""
+        n, h, w, _ = frames.shape
+        out = np.empty_like(frames) if out is None else out
+        self._check(self._lib.nv12eq_color_equalize_batch(self._h, _ptr(frames), _ptr(out), n, frames.strides[0], w, h,
+                                                          frames.strides[1], color_mode))
         return out
 
     def color_clahe(self, bgr: np.ndarray, clip_limit=3.0, tiles=(4, 4), color_mode: int = COLOR_YUV, out=None):

@@ -1098,6 +1098,17 @@ int nv12eq_color_equalize(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_o
     return run_batch(ctx, make_color_job(Op::ColorEq, bgr_in, bgr_out, width, height, stride, color_mode, 0, 0, 0));
 }
 
+int nv12eq_color_equalize_batch(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_out, int n_frames, size_t frame_pitch, int width,
+                                int height, int stride, int color_mode) {
+    int rc = check_color(ctx, width, height, stride, color_mode);
+    if (rc) return rc;
+    if (n_frames < 0 || (n_frames > 1 && frame_pitch < (size_t)stride * height)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad batch arguments");
+    Job j = make_color_job(Op::ColorEq, bgr_in, bgr_out, width, height, stride, color_mode, 0, 0, 0);
+    j.n = n_frames;
+    if (n_frames > 1) j.pitch = frame_pitch;
+    return run_batch(ctx, j);
+}
+
 int nv12eq_color_clahe(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_out, int width, int height, int stride, int color_mode,
                        double clip_limit, int tiles_x, int tiles_y) {
     int rc = check_color(ctx, width, height, stride, color_mode);

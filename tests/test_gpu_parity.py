@@ -426,3 +426,16 @@ def test_large_frames_many_frames_and_fine_grids(nv, oracle, torch):
         h_in, h_eq, h_cl = d_in.cpu().numpy().reshape(n, pitch), d_eq.cpu().numpy().reshape(n, pitch), d_cl.cpu().numpy().reshape(n, pitch)
         assert np.array_equal(h_eq, oracle.c_nv12_batch("equalize", h_in, W, H))
         assert np.array_equal(h_cl, oracle.c_nv12_batch("clahe", h_in, W, H, clip=2.0, tx=8, ty=8))
+
+
+def test_color_host_batch(nv, ctx, oracle):
+    """nv12eq_color_equalize_batch: several BGR frames per call, pipelined over the slots; pinned and pageable memory."""
+    W, H, n = 640, 360, 7
+    frames = np.stack([oracle.c_synth_bgr(W, H, k) for k in range(n)])
+    want = np.stack([oracle.c_color_equalize(frames[k], oracle.COLOR_YCRCB) for k in range(n)])
+    assert np.array_equal(ctx.color_equalize_batch(frames, nv.COLOR_YCRCB), want)
+    pin_in, pin_out = nv.PinnedBuffer(frames.nbytes), nv.PinnedBuffer(frames.nbytes)
+    pin_in.array[:] = frames.reshape(-1)
+    ctx.color_equalize_batch(pin_in.array.reshape(frames.shape), nv.COLOR_YCRCB, out=pin_out.array.reshape(frames.shape))
+    assert np.array_equal(pin_out.array.reshape(frames.shape), want)
+    pin_in.free(); pin_out.free()
