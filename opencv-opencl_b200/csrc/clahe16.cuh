@@ -1,24 +1,40 @@
 // clahe16.cuh -- CLAHE on CV_16UC1 planes (P010 luma and other 16-bit content): SURVEY.md section 8f rank 3.
 //
 // OpenCV's CLAHE accepts 16-bit input with histSize = 65536; the reference never feeds it 16-bit data, so this is a
-// widening row, built correctness-first: 65536-bin tile histograms and 128 KB tile LUTs do not fit shared memory, they
-// live in global memory and are served by L2.
-//   clahe16_hist_kernel   one CTA per (tile strip, frame): red.global.add into hist[frame][tile][65536]
-//                         (reflect-101 padding by index reflection, as in the 8-bit kernel)
-//   clahe16_lut_kernel    one CTA per (tile, frame): clip at clipLimit, redistribute the excess exactly as OpenCV
-//                         (redistBatch to every bin, +1 to every residualStep-th bin while the residual lasts), block-wide
-//                         scan, lut = saturate_cast<ushort>(cvRound(sum * lutScale)); returns the histogram to zero
-//   clahe16_interp_kernel per pixel: four 16-bit gathers from the neighbouring tile LUTs and OpenCV's blend op for op in
-//                         unfused fp32 (same weights and rounding as the 8-bit path)
-// Bound: L2 atomics (histogram) and L2 gathers (interpolation), not HBM; algorithmic bytes are 4*W*H per plane.
+// widening row.  65536-bin tile histograms (256 KB) and tile LUTs (128 KB) do not fit shared memory as they are; the
+// working set of one plane (histograms, LUTs, cell tables: ~66 MB for an 8x8 grid) is kept L2-resident by processing
+// few planes per pass.
+//   clahe16_hist_kernel        one CTA per (tile strip, tile, plane), 1024 threads, one CTA per SM: the strip's histogram is
+//                              built in 128 KB of shared memory as 65536 packed 16-bit counters (a strip has < 65536
+//                              pixels, so none overflows; the word index is XOR-swizzled so that P010's multiples of 64
+//                              do not all land in bank 0) and only the non-zero counters are added to the global
+//                              histogram (reflect-101 padding by index reflection, as in the 8-bit kernel)
+//   clahe16_lut_kernel         one cluster of 8 CTAs per tile, 8192 bins per CTA, one read of the histogram: clip, exchange
+//                              the partial sums through distributed shared memory, redistribute the excess exactly as
+//                              OpenCV does (redistBatch to every bin, +1 to every residualStep-th bin while the residual
+//                              lasts; the number of those bins in front of a part has a closed form), one block scan,
+//                              lut = saturate_cast<ushort>(cvRound(sum * lutScale)); returns the histogram to zero
+//   clahe16_cell_table_kernel  per interpolation cell (the region between four tile centres): table[v] =
+//                              {L11, L12, L21, L22}[v], 8 bytes, so that the blend needs ONE gather per pixel
+//   clahe16_interp_kernel      per pixel: one 8-byte gather and OpenCV's blend op for op in unfused fp32 (same weights and
+//                              rounding as the 8-bit path)
+// Bound: the gather (one distinct cache line per pixel through L1TEX) and the shared-memory atomics, not HBM;
+// algorithmic bytes are 4*W*H per plane.
 #pragma once
+#include <cooperative_groups.h>
 #include "clahe.cuh"
 
 namespace nv12eq {
 
 constexpr int kBins16 = 65536;
 constexpr int kC16Threads = 256;
-constexpr int kC16LutThreads = 1024;
+constexpr int kC16LutThreads = 512;
+constexpr int kC16BinsPerThread = 16;
+constexpr int kC16HistThreads = 1024;
+constexpr int kC16HistSmemBytes = kBins16 * 2;           // packed 16-bit counters
+constexpr int kC16StripPixels = 65535;                   // a 16-bit counter cannot overflow within one strip
+constexpr int kC16Parts = kBins16 / (kC16LutThreads * kC16BinsPerThread);  // 8 parts of 8192 bins: one cluster of 8 CTAs per tile
+constexpr int kC16PartBins = kBins16 / kC16Parts;
 
 struct Clahe16Params {
     const uint16_t* in;
@@ -31,27 +47,59 @@ struct Clahe16Params {
     float lut_scale, inv_tw, inv_th;
     uint32_t* hist;             // [n_planes][tx*ty][65536], zero on entry, zero again after clahe16_lut_kernel
     uint16_t* luts;             // [n_planes][tx*ty][65536]
-    int strips;                 // row strips per tile in the histogram kernel
+    uint2* cells;               // [n_planes][(ty+1)*(tx+1)][65536]: {L11 | L12 << 16, L21 | L22 << 16}
+    int strips, rows_strip;     // histogram kernel: row strips per tile, rows per strip
 };
 
-__global__ void __launch_bounds__(kC16Threads) clahe16_hist_kernel(const Clahe16Params p) {
+// word of the packed shared histogram that holds bins 2*w and 2*w + 1 (an involution: it is its own inverse)
+__device__ __forceinline__ uint32_t c16_swizzle(uint32_t w) { return w ^ ((w >> 5) & 31u) ^ ((w >> 10) & 31u); }
+__device__ __forceinline__ void c16_count(uint32_t* cnt, uint32_t v) {
+    atomicAdd(cnt + c16_swizzle(v >> 1), (v & 1u) ? 0x10000u : 1u);
+}
+__device__ __forceinline__ void c16_count2(uint32_t* cnt, uint32_t w) {
+    c16_count(cnt, w & 0xffffu);
+    c16_count(cnt, w >> 16);
+}
+
+__global__ void __launch_bounds__(kC16HistThreads, 1) clahe16_hist_kernel(const Clahe16Params p) {
+    uint32_t* cnt = nv12eq_smem_rows;   // 32768 words
     const int T = p.tx * p.ty;
     const int f = blockIdx.z, t = blockIdx.y, strip = blockIdx.x;
     const int tyi = t / p.tx, txi = t - tyi * p.tx;
     const int x0 = txi * p.tw, y0 = tyi * p.th;
-    const int rows_strip = (p.th + p.strips - 1) / p.strips;
-    const int r0 = strip * rows_strip, r1 = min(r0 + rows_strip, p.th);
+    const int r0 = strip * p.rows_strip, r1 = min(r0 + p.rows_strip, p.th);
+    if (r0 >= r1) return;
     const uint16_t* src = p.in + (unsigned long long)f * p.pitch;
     uint32_t* hist = p.hist + ((size_t)f * T + t) * kBins16;
-    const int n = (r1 - r0) * p.tw;
-    for (int i = threadIdx.x; i < n; i += kC16Threads) {
-        const int r = r0 + i / p.tw, c = i - (i / p.tw) * p.tw;
-        const uint16_t v = src[(size_t)reflect101(y0 + r, p.h) * p.stride + reflect101(x0 + c, p.w)];
-        atomicAdd(hist + v, 1u);
+    for (int i = threadIdx.x; i < kBins16 / 8; i += kC16HistThreads) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const bool vec = x0 + p.tw <= p.w && (p.tw & 7) == 0 && (p.stride & 7) == 0 && (((uintptr_t)src + 2 * (uintptr_t)x0) & 15) == 0;
+    if (vec) {
+        const int vpr = p.tw >> 3, n = (r1 - r0) * vpr;
+        for (int i = threadIdx.x; i < n; i += kC16HistThreads) {
+            const int r = i / vpr, c = i - r * vpr;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(y0 + r0 + r, p.h) * p.stride + x0) + c);
+            c16_count2(cnt, q.x); c16_count2(cnt, q.y); c16_count2(cnt, q.z); c16_count2(cnt, q.w);
+        }
+    } else {
+        const int n = (r1 - r0) * p.tw;
+        for (int i = threadIdx.x; i < n; i += kC16HistThreads) {
+            const int r = i / p.tw, c = i - r * p.tw;
+            c16_count(cnt, src[(size_t)reflect101(y0 + r0 + r, p.h) * p.stride + reflect101(x0 + c, p.w)]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBins16 / 2; i += kC16HistThreads) {
+        const uint32_t c = cnt[i];
+        if (c) {
+            const uint32_t b = c16_swizzle((uint32_t)i) * 2u;
+            if (c & 0xffffu) atomicAdd(hist + b, c & 0xffffu);
+            if (c >> 16) atomicAdd(hist + b + 1, c >> 16);
+        }
     }
 }
 
-// Block-wide inclusive scan of one int per thread (1024 threads); *total = sum over the block.
+// Block-wide inclusive scan of one int per thread (up to 1024 threads); *total = sum over the block.
 __device__ __forceinline__ int block_incl_scan(int v, int* s_warp, int* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = v;
@@ -63,7 +111,7 @@ __device__ __forceinline__ int block_incl_scan(int v, int* s_warp, int* total) {
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        const int w = s_warp[lane];
+        const int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
         int wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -80,72 +128,163 @@ __device__ __forceinline__ int block_incl_scan(int v, int* s_warp, int* total) {
     return r;
 }
 
-// One CTA per (tile, plane).  All accesses are coalesced: thread t owns bins t, t + 1024, ... (64 chunks of 1024 bins).
-__global__ void __launch_bounds__(kC16LutThreads) clahe16_lut_kernel(const Clahe16Params p) {
-    __shared__ int s_warp[33];
-    const int T = p.tx * p.ty;
-    const int f = blockIdx.y, t = blockIdx.x;
-    uint32_t* hist = p.hist + ((size_t)f * T + t) * kBins16;
-    uint16_t* lut = p.luts + ((size_t)f * T + t) * kBins16;
-    constexpr int kChunks = kBins16 / kC16LutThreads;
-    int batch = 0, residual = 0, step = 1;
-    uint32_t magic = 0;   // floor(2^32 / step) + 1: (i * magic) >> 32 == i / step for i < 65536, 2 <= step <= 65536
-    if (p.clip_limit > 0) {
-        int part = 0;     // a tile has fewer than 2^31 pixels: int sums are safe
-#pragma unroll 4
-        for (int c = 0; c < kChunks; ++c) part += max((int)hist[c * kC16LutThreads + threadIdx.x] - p.clip_limit, 0);
-        int clipped;
-        block_incl_scan(part, s_warp, &clipped);
-        batch = clipped / kBins16;
-        residual = clipped - batch * kBins16;
-        if (residual != 0) step = max(kBins16 / residual, 1);
-        if (step > 1) magic = (uint32_t)(0x100000000ull / (uint32_t)step) + 1u;
+// Sum of an int pair over the block (up to 1024 threads); valid in every thread.
+__device__ __forceinline__ int2 block_sum2(int a, int b, int* s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d);
+        b += __shfl_xor_sync(0xffffffffu, b, d);
     }
-    int carry = 0;
-    for (int c = 0; c < kChunks; ++c) {
-        const int i = c * kC16LutThreads + threadIdx.x;
-        int hv = (int)hist[i];
-        hist[i] = 0;      // ready for the next launch
+    if (lane == 0) { s_warp[warp] = a; s_warp[32 + warp] = b; }
+    __syncthreads();
+    const bool live = lane < (int)(blockDim.x >> 5);
+    a = live ? s_warp[lane] : 0; b = live ? s_warp[32 + lane] : 0;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d);
+        b += __shfl_xor_sync(0xffffffffu, b, d);
+    }
+    return make_int2(a, b);
+}
+
+// number of k in [0, residual) with lo <= k * step < hi
+__device__ __forceinline__ int c16_residual_bins(int lo, int hi, int step, int residual) {
+    const int ka = (lo + step - 1) / step, kb = (hi + step - 1) / step;
+    return max(min(kb, residual) - ka, 0);
+}
+
+// grid (kC16Parts, tiles, planes) in clusters of kC16Parts CTAs: one cluster per tile histogram, one CTA per part of
+// 8192 bins, thread t owns bins 16t .. 16t+15 of its part (64 bytes in, 32 bytes out; four CTAs per SM).  The parts exchange their sums
+// through distributed shared memory: the clip pass, the redistribution and the scan need one read of the histogram.
+__global__ void __cluster_dims__(kC16Parts, 1, 1) __launch_bounds__(kC16LutThreads) clahe16_lut_kernel(const Clahe16Params p) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ int s_warp[64];
+    __shared__ int2 s_part;     // (sum of min(h, clip), clipped excess) of this part; read by the whole cluster
+    __shared__ int s_hdr[4];    // batch, residual, step, histogram mass in front of this part
+    const int T = p.tx * p.ty;
+    const int part = blockIdx.x, t = blockIdx.y, f = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* hist = p.hist + ((size_t)f * T + t) * kBins16 + part * kC16PartBins;
+    uint16_t* lut = p.luts + ((size_t)f * T + t) * kBins16 + part * kC16PartBins;
+    constexpr int B = kC16BinsPerThread;
+    int h[B];
+#pragma unroll
+    for (int j = 0; j < B / 4; ++j) {
+        uint4* q = reinterpret_cast<uint4*>(hist) + threadIdx.x * (B / 4) + j;
+        const uint4 r = *q;
+        *q = make_uint4(0, 0, 0, 0);   // ready for the next launch
+        h[4 * j] = (int)r.x; h[4 * j + 1] = (int)r.y; h[4 * j + 2] = (int)r.z; h[4 * j + 3] = (int)r.w;
+    }
+    int kept = 0, excess = 0;   // a tile has fewer than 2^31 pixels: int sums are safe
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        if (p.clip_limit > 0) { excess += max(h[j] - p.clip_limit, 0); h[j] = min(h[j], p.clip_limit); }
+        kept += h[j];
+    }
+    const int2 mine = block_sum2(kept, excess, s_warp);
+    if (threadIdx.x == 0) s_part = mine;
+    cluster.sync();
+    if (warp == 0) {
+        int2 v = make_int2(0, 0);
+        if (lane < kC16Parts) v = *cluster.map_shared_rank(&s_part, lane);
+        int clipped = v.y;
+#pragma unroll
+        for (int d = kC16Parts / 2; d >= 1; d >>= 1) clipped += __shfl_xor_sync(0xffffffffu, clipped, d);
+        const int batch = clipped / kBins16;
+        const int residual = clipped - batch * kBins16;
+        const int step = residual != 0 ? max(kBins16 / residual, 1) : 1;
+        int before = lane < part ? v.x + batch * kC16PartBins + c16_residual_bins(lane * kC16PartBins, (lane + 1) * kC16PartBins, step, residual) : 0;
+#pragma unroll
+        for (int d = kC16Parts / 2; d >= 1; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
+        if (lane == 0) { s_hdr[0] = batch; s_hdr[1] = residual; s_hdr[2] = step; s_hdr[3] = before; }
+    }
+    __syncthreads();
+    const int batch = s_hdr[0], residual = s_hdr[1], step = s_hdr[2], prefix = s_hdr[3];
+    // floor(2^32 / step) + 1 in 32-bit arithmetic: (i * magic) >> 32 == i / step for i < 65536, 2 <= step <= 65536
+    const uint32_t magic = step > 1 ? 0xffffffffu / (uint32_t)step + 1u + ((step & (step - 1)) == 0 ? 1u : 0u) : 0u;
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
         if (p.clip_limit > 0) {
-            hv = min(hv, p.clip_limit) + batch;
+            const int i = part * kC16PartBins + threadIdx.x * B + j;
+            h[j] += batch;
             // for (i = 0; i < histSize && residual > 0; i += step, residual--) h[i]++
             if (residual != 0) {
                 const int q = step > 1 ? (int)(((unsigned long long)(uint32_t)i * magic) >> 32) : i;
-                if (q * step == i && q < residual) hv += 1;
+                if (q * step == i && q < residual) h[j] += 1;
             }
         }
-        int chunk_total;
-        const int run = carry + block_incl_scan(hv, s_warp, &chunk_total);
-        carry += chunk_total;
-        const int r = __float2int_rn(__fmul_rn(__int2float_rn(run), p.lut_scale));
-        lut[i] = (uint16_t)min(max(r, 0), 65535);
+        sum += h[j];
     }
+    int part_total;
+    int run = prefix + block_incl_scan(sum, s_warp, &part_total) - sum;
+#pragma unroll
+    for (int j = 0; j < B / 8; ++j) {
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            run += h[8 * j + k];
+            o[k] = (uint32_t)min(max(__float2int_rn(__fmul_rn(__int2float_rn(run), p.lut_scale)), 0), 65535);
+        }
+        reinterpret_cast<uint4*>(lut)[threadIdx.x * (B / 8) + j] = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
+    }
+    cluster.sync();   // s_part must outlive the remote reads of the other CTAs
 }
 
-__global__ void __launch_bounds__(kC16Threads) clahe16_interp_kernel(const Clahe16Params p) {
-    const int T = p.tx * p.ty;
-    const int f = blockIdx.z, y = blockIdx.y;
-    const uint16_t* src = p.in + (unsigned long long)f * p.pitch + (size_t)y * p.stride;
-    uint16_t* dst = p.out + (unsigned long long)f * p.pitch + (size_t)y * p.stride;
+// grid (65536 / 1024, cells, planes), 256 threads x 4 values: the four tile LUTs a cell blends, interleaved per value.
+// Cell (cy, cx) lies between tile rows cy-1, cy and tile columns cx-1, cx (clamped to the grid).
+__global__ void __launch_bounds__(kC16Threads) clahe16_cell_table_kernel(const Clahe16Params p) {
+    const int T = p.tx * p.ty, ncx = p.tx + 1;
+    const int cell = blockIdx.y, f = blockIdx.z;
+    const int cy = cell / ncx, cx = cell - cy * ncx;
+    const int ty1 = max(cy - 1, 0), ty2 = min(cy, p.ty - 1), tx1 = max(cx - 1, 0), tx2 = min(cx, p.tx - 1);
     const uint16_t* luts = p.luts + (size_t)f * T * kBins16;
-    float ya, ya1;
-    axis_weight(y, p.inv_th, ya, ya1);
-    const int tyf = (int)floorf(__fsub_rn(__fmul_rn((float)y, p.inv_th), 0.5f));
-    const int ty1 = max(tyf, 0), ty2 = min(tyf + 1, p.ty - 1);
-    for (int x = blockIdx.x * kC16Threads + threadIdx.x; x < p.w; x += gridDim.x * kC16Threads) {
-        float xa, xa1;
-        axis_weight(x, p.inv_tw, xa, xa1);
-        const int txf = (int)floorf(__fsub_rn(__fmul_rn((float)x, p.inv_tw), 0.5f));
-        const int tx1 = max(txf, 0), tx2 = min(txf + 1, p.tx - 1);
-        const uint32_t v = src[x];
-        const float l11 = (float)__ldg(luts + (size_t)(ty1 * p.tx + tx1) * kBins16 + v);
-        const float l12 = (float)__ldg(luts + (size_t)(ty1 * p.tx + tx2) * kBins16 + v);
-        const float l21 = (float)__ldg(luts + (size_t)(ty2 * p.tx + tx1) * kBins16 + v);
-        const float l22 = (float)__ldg(luts + (size_t)(ty2 * p.tx + tx2) * kBins16 + v);
-        const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
-        const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-        const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-        dst[x] = (uint16_t)min(max(__float2int_rn(res), 0), 65535);
+    const int v4 = blockIdx.x * kC16Threads + threadIdx.x;   // values 4*v4 .. 4*v4+3
+    const uint2 a = reinterpret_cast<const uint2*>(luts + (size_t)(ty1 * p.tx + tx1) * kBins16)[v4];
+    const uint2 b = reinterpret_cast<const uint2*>(luts + (size_t)(ty1 * p.tx + tx2) * kBins16)[v4];
+    const uint2 c = reinterpret_cast<const uint2*>(luts + (size_t)(ty2 * p.tx + tx1) * kBins16)[v4];
+    const uint2 d = reinterpret_cast<const uint2*>(luts + (size_t)(ty2 * p.tx + tx2) * kBins16)[v4];
+    uint4* dst = reinterpret_cast<uint4*>(p.cells + ((size_t)f * (p.ty + 1) * ncx + cell) * kBins16) + (size_t)v4 * 2;
+    // lo(x, y) = low halves of x and y packed, hi(x, y) = high halves
+    dst[0] = make_uint4(__byte_perm(a.x, b.x, 0x5410), __byte_perm(c.x, d.x, 0x5410), __byte_perm(a.x, b.x, 0x7632), __byte_perm(c.x, d.x, 0x7632));
+    dst[1] = make_uint4(__byte_perm(a.y, b.y, 0x5410), __byte_perm(c.y, d.y, 0x5410), __byte_perm(a.y, b.y, 0x7632), __byte_perm(c.y, d.y, 0x7632));
+}
+
+constexpr int kC16RowsPerCta = 8;
+
+// grid (ceil(w / 256), ceil(h / 8), planes): a thread owns one column of 8 rows, so the x weights are computed once.
+__global__ void __launch_bounds__(kC16Threads) clahe16_interp_kernel(const Clahe16Params p) {
+    const int ncx = p.tx + 1;
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * kC16Threads + threadIdx.x;
+    if (x >= p.w) return;
+    float xa, xa1;
+    axis_weight(x, p.inv_tw, xa, xa1);
+    const int cx = (int)floorf(__fsub_rn(__fmul_rn((float)x, p.inv_tw), 0.5f)) + 1;   // 0 .. tx
+    const uint2* cells = p.cells + (size_t)f * (p.ty + 1) * ncx * kBins16;
+    const int y0 = blockIdx.y * kC16RowsPerCta, y1 = min(y0 + kC16RowsPerCta, p.h);
+    const uint16_t* src = p.in + (unsigned long long)f * p.pitch + x;
+    uint16_t* dst = p.out + (unsigned long long)f * p.pitch + x;
+    uint32_t v[kC16RowsPerCta];
+#pragma unroll
+    for (int k = 0; k < kC16RowsPerCta; ++k) v[k] = y0 + k < y1 ? src[(size_t)(y0 + k) * p.stride] : 0u;
+#pragma unroll
+    for (int k = 0; k < kC16RowsPerCta; ++k) {
+        const int y = y0 + k;
+        if (y < y1) {
+            float ya, ya1;
+            axis_weight(y, p.inv_th, ya, ya1);
+            const int cy = (int)floorf(__fsub_rn(__fmul_rn((float)y, p.inv_th), 0.5f)) + 1;   // 0 .. ty
+            const uint2 e = __ldg(cells + (size_t)(cy * ncx + cx) * kBins16 + v[k]);
+            const float l11 = (float)(e.x & 0xffffu), l12 = (float)(e.x >> 16);
+            const float l21 = (float)(e.y & 0xffffu), l22 = (float)(e.y >> 16);
+            const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+            const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+            const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+            dst[(size_t)y * p.stride] = (uint16_t)min(max(__float2int_rn(res), 0), 65535);
+        }
     }
 }
 

@@ -70,6 +70,7 @@ struct Workspace {
     DevBuf luma;      // colour: [2][frames][h][w]
     DevBuf hist16;    // clahe16: [planes][tiles][65536] u32, kept zero between launches
     DevBuf luts16;    // clahe16: [planes][tiles][65536] u16
+    DevBuf cells16;   // clahe16: [planes][cells][65536] four u16 per value
     int frames_cap = 0;
     // cached CLAHE geometry
     int gw = 0, gh = 0, gtx = 0, gty = 0, nxc = 0, nyc = 0;
@@ -248,7 +249,7 @@ void host_release(HostBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap
 
 void ws_release(Workspace& w) {
     dev_release(w.hist); dev_release(w.counters); dev_release(w.misc); dev_release(w.luts); dev_release(w.cells);
-    dev_release(w.luma); dev_release(w.hist16); dev_release(w.luts16);
+    dev_release(w.luma); dev_release(w.hist16); dev_release(w.luts16); dev_release(w.cells16);
     w.frames_cap = 0; w.gw = w.gh = w.gtx = w.gty = 0;
 }
 
@@ -279,6 +280,7 @@ int ensure_attrs(nv12eq_ctx* ctx) {
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(equalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneTableBytes));
     CK(ctx, cudaFuncSetAttribute(color_equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kColorEqSmemBytes));
+    CK(ctx, cudaFuncSetAttribute(clahe16_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC16HistSmemBytes));
     CK(ctx, cudaFuncSetAttribute(clahe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
     CK(ctx, cudaFuncSetAttribute(clahe_kernel<kClaheCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
     CK(ctx, cudaFuncSetAttribute(clahe_kernel<kClaheCtas - 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClaheSmemBytes));
@@ -1222,22 +1224,34 @@ static int launch_clahe16(nv12eq_ctx* ctx, Workspace& ws, const uint16_t* d_in, 
     p.clip_limit = clip > 0.0 ? std::max(1, (int)(clip * area / 65536.0)) : 0;
     p.lut_scale = 65535.0f / (float)area;
     p.inv_tw = 1.0f / (float)p.tw; p.inv_th = 1.0f / (float)p.th;
-    // planes per pass: histograms are 256 KB per tile; keep the workspace near 256 MB
-    const int group = std::max(1, std::min(n, 1024 / T));
-    int rc = dev_reserve(ctx, ws.hist16, (size_t)group * T * kBins16 * sizeof(uint32_t), true);
+    if (p.tw > kC16StripPixels) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "16-bit tile rows of %d pixels are not supported", p.tw);
+    // planes per pass: one plane's histograms (256 KB per tile), LUTs (128 KB per tile) and cell tables (512 KB per cell)
+    // should stay L2-resident between the kernels, so a pass takes few planes -- just enough tiles to fill the GPU
+    const int cells = (tx + 1) * (ty + 1);
+    const int group = std::max(1, std::min(n, 64 / T));
+    int rc = ensure_attrs(ctx);
+    if (rc) return rc;
+    rc = dev_reserve(ctx, ws.hist16, (size_t)group * T * kBins16 * sizeof(uint32_t), true);
     if (rc) return rc;
     if ((rc = dev_reserve(ctx, ws.luts16, (size_t)group * T * kBins16 * sizeof(uint16_t), false))) return rc;
+    if ((rc = dev_reserve(ctx, ws.cells16, (size_t)group * cells * kBins16 * sizeof(uint2), false))) return rc;
     p.hist = reinterpret_cast<uint32_t*>(ws.hist16.p);
     p.luts = reinterpret_cast<uint16_t*>(ws.luts16.p);
+    p.cells = reinterpret_cast<uint2*>(ws.cells16.p);
     for (int g0 = 0; g0 < n; g0 += group) {
         const int ng = std::min(group, n - g0);
         p.in = d_in + (size_t)g0 * pitch; p.out = d_out + (size_t)g0 * pitch; p.n_planes = ng;
-        p.strips = (int)std::max<long long>(1, std::min<long long>(p.th, ((long long)ctx->sm_count * 8 + (long long)T * ng - 1) / ((long long)T * ng)));
-        clahe16_hist_kernel<<<dim3(p.strips, T, ng), kC16Threads, 0, st>>>(p);
-        clahe16_lut_kernel<<<dim3(T, ng), kC16LutThreads, 0, st>>>(p);
-        const int gx = std::max(1, std::min((w + kC16Threads - 1) / kC16Threads, 64));
-        clahe16_interp_kernel<<<dim3(gx, h, ng), kC16Threads, 0, st>>>(p);
-        ctx->ctr.kernel_launches += 3;
+        // strips: short enough for 16-bit counters; one CTA runs per SM, so as many strips as fit into one wave (every
+        // further strip costs another zeroing and flush of the 128 KB counter table)
+        const int max_rows = std::max(1, kC16StripPixels / p.tw);
+        const long long want = std::max<long long>(1, (long long)ctx->sm_count / ((long long)T * ng));
+        p.rows_strip = (int)std::max<long long>(1, std::min<long long>(max_rows, (p.th + want - 1) / want));
+        p.strips = (p.th + p.rows_strip - 1) / p.rows_strip;
+        clahe16_hist_kernel<<<dim3(p.strips, T, ng), kC16HistThreads, kC16HistSmemBytes, st>>>(p);
+        clahe16_lut_kernel<<<dim3(kC16Parts, T, ng), kC16LutThreads, 0, st>>>(p);
+        clahe16_cell_table_kernel<<<dim3(kBins16 / (kC16Threads * 4), cells, ng), kC16Threads, 0, st>>>(p);
+        clahe16_interp_kernel<<<dim3((w + kC16Threads - 1) / kC16Threads, (h + kC16RowsPerCta - 1) / kC16RowsPerCta, ng), kC16Threads, 0, st>>>(p);
+        ctx->ctr.kernel_launches += 4;
         CK(ctx, cudaGetLastError());
     }
     return NV12EQ_OK;
