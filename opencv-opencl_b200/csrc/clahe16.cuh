@@ -46,19 +46,27 @@ struct Clahe16Params {
     int clip_limit;
     float lut_scale, inv_tw, inv_th;
     uint32_t* hist;             // [n_planes][tx*ty][65536], zero on entry, zero again after clahe16_lut_kernel
-    uint16_t* luts;             // [n_planes][tx*ty][65536]
-    uint2* cells;               // [n_planes][(ty+1)*(tx+1)][65536]: {L11 | L12 << 16, L21 | L22 << 16}
+    uint16_t* luts;             // [n_planes][tx*ty][65536], compact: entry k is the LUT value of k << z
+    uint2* cells;               // [n_planes][(ty+1)*(tx+1)][65536]: {L11 | L12 << 16, L21 | L22 << 16} at index v >> z
+    uint32_t* ormask;           // [n_planes]: OR of all pixel values of the plane (zero on entry to the histogram kernel)
     int strips, rows_strip;     // histogram kernel: row strips per tile, rows per strip
 };
 
 // word of the packed shared histogram that holds bins 2*w and 2*w + 1 (an involution: it is its own inverse)
-__device__ __forceinline__ uint32_t c16_swizzle(uint32_t w) { return w ^ ((w >> 5) & 31u) ^ ((w >> 10) & 31u); }
+__device__ __forceinline__ uint32_t c16_swizzle(uint32_t w) { return w ^ ((w >> 5) & 31u); }
 __device__ __forceinline__ void c16_count(uint32_t* cnt, uint32_t v) {
     atomicAdd(cnt + c16_swizzle(v >> 1), (v & 1u) ? 0x10000u : 1u);
 }
 __device__ __forceinline__ void c16_count2(uint32_t* cnt, uint32_t w) {
     c16_count(cnt, w & 0xffffu);
     c16_count(cnt, w >> 16);
+}
+// Number of low bits that are zero in every pixel of the plane (P010: 6, 12-bit content in 16-bit words: 4, full range: 0).
+// Only the LUT entries v = k << z can ever be looked up, so the cell tables are built and indexed at v >> z: for 10-bit
+// video that is 8 KB per cell instead of 512 KB, and neighbouring grey levels share cache lines.
+__device__ __forceinline__ int c16_zero_bits(uint32_t ormask) {
+    const uint32_t m = ormask & 0xffffu;
+    return m ? __ffs((int)m) - 1 : 16;
 }
 
 __global__ void __launch_bounds__(kC16HistThreads, 1) clahe16_hist_kernel(const Clahe16Params p) {
@@ -71,24 +79,44 @@ __global__ void __launch_bounds__(kC16HistThreads, 1) clahe16_hist_kernel(const 
     if (r0 >= r1) return;
     const uint16_t* src = p.in + (unsigned long long)f * p.pitch;
     uint32_t* hist = p.hist + ((size_t)f * T + t) * kBins16;
+    __shared__ uint32_t s_seen;
+    if (threadIdx.x == 0) s_seen = 0;
+    uint32_t seen = 0;
     for (int i = threadIdx.x; i < kBins16 / 8; i += kC16HistThreads) reinterpret_cast<uint4*>(cnt)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const bool vec = x0 + p.tw <= p.w && (p.tw & 7) == 0 && (p.stride & 7) == 0 && (((uintptr_t)src + 2 * (uintptr_t)x0) & 15) == 0;
     if (vec) {
         const int vpr = p.tw >> 3, n = (r1 - r0) * vpr;
-        for (int i = threadIdx.x; i < n; i += kC16HistThreads) {
+        auto load = [&](int i) {
             const int r = i / vpr, c = i - r * vpr;
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(y0 + r0 + r, p.h) * p.stride + x0) + c);
+            return __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(y0 + r0 + r, p.h) * p.stride + x0) + c);
+        };
+        // two vectors in flight per thread: the loads of the next round overlap the shared atomics of this one
+        int i = threadIdx.x;
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+        if (i < n) q0 = load(i);
+        if (i + kC16HistThreads < n) q1 = load(i + kC16HistThreads);
+        while (i < n) {
+            const uint4 q = q0;
+            q0 = q1;
+            if (i + 2 * kC16HistThreads < n) q1 = load(i + 2 * kC16HistThreads);
+            seen |= q.x | q.y | q.z | q.w;
             c16_count2(cnt, q.x); c16_count2(cnt, q.y); c16_count2(cnt, q.z); c16_count2(cnt, q.w);
+            i += kC16HistThreads;
         }
     } else {
         const int n = (r1 - r0) * p.tw;
         for (int i = threadIdx.x; i < n; i += kC16HistThreads) {
             const int r = i / p.tw, c = i - r * p.tw;
-            c16_count(cnt, src[(size_t)reflect101(y0 + r0 + r, p.h) * p.stride + reflect101(x0 + c, p.w)]);
+            const uint32_t v = src[(size_t)reflect101(y0 + r0 + r, p.h) * p.stride + reflect101(x0 + c, p.w)];
+            seen |= v;
+            c16_count(cnt, v);
         }
     }
+    seen = __reduce_or_sync(0xffffffffu, (seen | (seen >> 16)) & 0xffffu);
+    if ((threadIdx.x & 31) == 0 && (seen & ~s_seen) != 0) atomicOr(&s_seen, seen);
     __syncthreads();
+    if (threadIdx.x == 0 && s_seen != 0) atomicOr(p.ormask + f, s_seen);
     for (int i = threadIdx.x; i < kBins16 / 2; i += kC16HistThreads) {
         const uint32_t c = cnt[i];
         if (c) {
@@ -148,34 +176,39 @@ __device__ __forceinline__ int2 block_sum2(int a, int b, int* s_warp) {
     return make_int2(a, b);
 }
 
-// number of k in [0, residual) with lo <= k * step < hi
-__device__ __forceinline__ int c16_residual_bins(int lo, int hi, int step, int residual) {
-    const int ka = (lo + step - 1) / step, kb = (hi + step - 1) / step;
-    return max(min(kb, residual) - ka, 0);
-}
-
-// grid (kC16Parts, tiles, planes) in clusters of kC16Parts CTAs: one cluster per tile histogram, one CTA per part of
-// 8192 bins, thread t owns bins 16t .. 16t+15 of its part (64 bytes in, 32 bytes out; four CTAs per SM).  The parts exchange their sums
-// through distributed shared memory: the clip pass, the redistribution and the scan need one read of the histogram.
-__global__ void __cluster_dims__(kC16Parts, 1, 1) __launch_bounds__(kC16LutThreads) clahe16_lut_kernel(const Clahe16Params p) {
+// grid (kC16Parts, tiles, planes) in clusters of kC16Parts CTAs: one cluster per tile histogram.  Only the bins v = k << z
+// (z = c16_zero_bits of the plane, k < 65536 >> z) can be non-zero and only their LUT entries can be looked up, so the
+// kernel works on those "compact" bins: CTA `part` owns compact bins [8192 part, 8192 (part + 1)), thread t 16 of them.
+// The parts exchange their sums through distributed shared memory, so the histogram is read once.  OpenCV's
+// redistribution (redistBatch to every one of the 65536 bins, +1 to bins 0, step, 2 step, ... while the residual lasts)
+// has a closed form for the cumulative sum at bin v:
+//     cum(v) = sum_{u <= v} min(h[u], clip)  +  redistBatch * (v + 1)  +  min(residual, v / step + 1)   [last term if residual > 0]
+// The LUT is written compact: entry k of a tile's table holds the value for v = k << z.
+__global__ void __cluster_dims__(kC16Parts, 1, 1) __launch_bounds__(kC16LutThreads, 3) clahe16_lut_kernel(const Clahe16Params p) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ int s_warp[64];
     __shared__ int2 s_part;     // (sum of min(h, clip), clipped excess) of this part; read by the whole cluster
-    __shared__ int s_hdr[4];    // batch, residual, step, histogram mass in front of this part
+    __shared__ int s_hdr[4];    // batch, residual, step, clipped histogram mass in front of this part
     const int T = p.tx * p.ty;
     const int part = blockIdx.x, t = blockIdx.y, f = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* hist = p.hist + ((size_t)f * T + t) * kBins16 + part * kC16PartBins;
-    uint16_t* lut = p.luts + ((size_t)f * T + t) * kBins16 + part * kC16PartBins;
+    const int z = c16_zero_bits(__ldg(p.ormask + f));
+    const int nb = kBins16 >> z;
     constexpr int B = kC16BinsPerThread;
+    const int k0 = part * kC16PartBins + threadIdx.x * B;   // first compact bin of this thread
+    uint32_t* hist = p.hist + ((size_t)f * T + t) * kBins16;
+    uint16_t* lut = p.luts + ((size_t)f * T + t) * kBins16;
     int h[B];
+    if (z == 0) {
 #pragma unroll
-    for (int j = 0; j < B / 4; ++j) {
-        uint4* q = reinterpret_cast<uint4*>(hist) + threadIdx.x * (B / 4) + j;
-        const uint4 r = *q;
-        *q = make_uint4(0, 0, 0, 0);   // ready for the next launch
-        h[4 * j] = (int)r.x; h[4 * j + 1] = (int)r.y; h[4 * j + 2] = (int)r.z; h[4 * j + 3] = (int)r.w;
+        for (int j = 0; j < B / 4; ++j) {
+            const uint4 r = reinterpret_cast<const uint4*>(hist + k0)[j];
+            h[4 * j] = (int)r.x; h[4 * j + 1] = (int)r.y; h[4 * j + 2] = (int)r.z; h[4 * j + 3] = (int)r.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < B; ++j) h[j] = k0 + j < nb ? (int)hist[(size_t)(k0 + j) << z] : 0;
     }
     int kept = 0, excess = 0;   // a tile has fewer than 2^31 pixels: int sums are safe
 #pragma unroll
@@ -185,105 +218,137 @@ __global__ void __cluster_dims__(kC16Parts, 1, 1) __launch_bounds__(kC16LutThrea
     }
     const int2 mine = block_sum2(kept, excess, s_warp);
     if (threadIdx.x == 0) s_part = mine;
-    cluster.sync();
+    cluster.sync();   // release/acquire on s_part; no global store is pending yet, so the fence is cheap
     if (warp == 0) {
         int2 v = make_int2(0, 0);
         if (lane < kC16Parts) v = *cluster.map_shared_rank(&s_part, lane);
         int clipped = v.y;
+        int before = lane < part ? v.x : 0;
 #pragma unroll
-        for (int d = kC16Parts / 2; d >= 1; d >>= 1) clipped += __shfl_xor_sync(0xffffffffu, clipped, d);
+        for (int d = kC16Parts / 2; d >= 1; d >>= 1) {
+            clipped += __shfl_xor_sync(0xffffffffu, clipped, d);
+            before += __shfl_xor_sync(0xffffffffu, before, d);
+        }
         const int batch = clipped / kBins16;
         const int residual = clipped - batch * kBins16;
-        const int step = residual != 0 ? max(kBins16 / residual, 1) : 1;
-        int before = lane < part ? v.x + batch * kC16PartBins + c16_residual_bins(lane * kC16PartBins, (lane + 1) * kC16PartBins, step, residual) : 0;
-#pragma unroll
-        for (int d = kC16Parts / 2; d >= 1; d >>= 1) before += __shfl_xor_sync(0xffffffffu, before, d);
-        if (lane == 0) { s_hdr[0] = batch; s_hdr[1] = residual; s_hdr[2] = step; s_hdr[3] = before; }
+        if (lane == 0) { s_hdr[0] = batch; s_hdr[1] = residual; s_hdr[2] = residual != 0 ? max(kBins16 / residual, 1) : 1; s_hdr[3] = before; }
     }
     __syncthreads();
-    const int batch = s_hdr[0], residual = s_hdr[1], step = s_hdr[2], prefix = s_hdr[3];
-    // floor(2^32 / step) + 1 in 32-bit arithmetic: (i * magic) >> 32 == i / step for i < 65536, 2 <= step <= 65536
-    const uint32_t magic = step > 1 ? 0xffffffffu / (uint32_t)step + 1u + ((step & (step - 1)) == 0 ? 1u : 0u) : 0u;
-    int sum = 0;
+    // the remote reads of this CTA are done: arrive now, wait at the very end (s_part must outlive the other CTAs' reads);
+    // relaxed, because nothing written after this point is read inside the cluster
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    // histogram back to zero, ready for the next launch
+    if (z == 0) {
 #pragma unroll
-    for (int j = 0; j < B; ++j) {
-        if (p.clip_limit > 0) {
-            const int i = part * kC16PartBins + threadIdx.x * B + j;
-            h[j] += batch;
-            // for (i = 0; i < histSize && residual > 0; i += step, residual--) h[i]++
-            if (residual != 0) {
-                const int q = step > 1 ? (int)(((unsigned long long)(uint32_t)i * magic) >> 32) : i;
-                if (q * step == i && q < residual) h[j] += 1;
-            }
-        }
-        sum += h[j];
+        for (int j = 0; j < B / 4; ++j) reinterpret_cast<uint4*>(hist + k0)[j] = make_uint4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+            if (k0 + j < nb) hist[(size_t)(k0 + j) << z] = 0;
     }
+    const int batch = s_hdr[0], residual = s_hdr[1], step = s_hdr[2];
+    // floor(2^32 / step) + 1 in 32-bit arithmetic: (v * magic) >> 32 == v / step for v < 65536, 2 <= step <= 65536
+    const uint32_t magic = step > 1 ? 0xffffffffu / (uint32_t)step + 1u + ((step & (step - 1)) == 0 ? 1u : 0u) : 0u;
     int part_total;
-    int run = prefix + block_incl_scan(sum, s_warp, &part_total) - sum;
+    int run = s_hdr[3] + block_incl_scan(kept, s_warp, &part_total) - kept;
+    const bool whole = k0 + B <= nb;
 #pragma unroll
-    for (int j = 0; j < B / 8; ++j) {
+    for (int j8 = 0; j8 < B; j8 += 8) {
         uint32_t o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            run += h[8 * j + k];
-            o[k] = (uint32_t)min(max(__float2int_rn(__fmul_rn(__int2float_rn(run), p.lut_scale)), 0), 65535);
+        for (int j = 0; j < 8; ++j) {
+            run += h[j8 + j];
+            const uint32_t v = (uint32_t)(k0 + j8 + j) << z;   // < 65536 for every bin that is stored
+            const int vq = step > 1 ? (int)(((unsigned long long)v * magic) >> 32) : (int)v;
+            const int cum = run + batch * (int)(v + 1u) + (residual != 0 ? min(residual, vq + 1) : 0);
+            o[j] = (uint32_t)min(max(__float2int_rn(__fmul_rn(__int2float_rn(cum), p.lut_scale)), 0), 65535);
         }
-        reinterpret_cast<uint4*>(lut)[threadIdx.x * (B / 8) + j] = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
+        if (whole) {
+            *reinterpret_cast<uint4*>(lut + k0 + j8) = make_uint4(o[0] | (o[1] << 16), o[2] | (o[3] << 16), o[4] | (o[5] << 16), o[6] | (o[7] << 16));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (k0 + j8 + j < nb) lut[k0 + j8 + j] = (uint16_t)o[j];
+        }
     }
-    cluster.sync();   // s_part must outlive the remote reads of the other CTAs
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
 }
 
-// grid (65536 / 1024, cells, planes), 256 threads x 4 values: the four tile LUTs a cell blends, interleaved per value.
-// Cell (cy, cx) lies between tile rows cy-1, cy and tile columns cx-1, cx (clamped to the grid).
+// grid (65536 / 1024, cells, planes), 256 threads x 4 table entries: the four tile LUTs a cell blends, interleaved per
+// value.  Cell (cy, cx) lies between tile rows cy-1, cy and tile columns cx-1, cx (clamped to the grid).  Like the tile
+// LUTs the table is compact: entry k holds value k << z (see c16_zero_bits), entries past 65536 >> z do not exist.
 __global__ void __launch_bounds__(kC16Threads) clahe16_cell_table_kernel(const Clahe16Params p) {
     const int T = p.tx * p.ty, ncx = p.tx + 1;
     const int cell = blockIdx.y, f = blockIdx.z;
+    const int z = c16_zero_bits(__ldg(p.ormask + f));
+    const int v4 = blockIdx.x * kC16Threads + threadIdx.x;   // entries 4*v4 .. 4*v4+3
+    if (4 * v4 >= (kBins16 >> z)) return;
     const int cy = cell / ncx, cx = cell - cy * ncx;
     const int ty1 = max(cy - 1, 0), ty2 = min(cy, p.ty - 1), tx1 = max(cx - 1, 0), tx2 = min(cx, p.tx - 1);
     const uint16_t* luts = p.luts + (size_t)f * T * kBins16;
-    const int v4 = blockIdx.x * kC16Threads + threadIdx.x;   // values 4*v4 .. 4*v4+3
-    const uint2 a = reinterpret_cast<const uint2*>(luts + (size_t)(ty1 * p.tx + tx1) * kBins16)[v4];
-    const uint2 b = reinterpret_cast<const uint2*>(luts + (size_t)(ty1 * p.tx + tx2) * kBins16)[v4];
-    const uint2 c = reinterpret_cast<const uint2*>(luts + (size_t)(ty2 * p.tx + tx1) * kBins16)[v4];
-    const uint2 d = reinterpret_cast<const uint2*>(luts + (size_t)(ty2 * p.tx + tx2) * kBins16)[v4];
-    uint4* dst = reinterpret_cast<uint4*>(p.cells + ((size_t)f * (p.ty + 1) * ncx + cell) * kBins16) + (size_t)v4 * 2;
-    // lo(x, y) = low halves of x and y packed, hi(x, y) = high halves
-    dst[0] = make_uint4(__byte_perm(a.x, b.x, 0x5410), __byte_perm(c.x, d.x, 0x5410), __byte_perm(a.x, b.x, 0x7632), __byte_perm(c.x, d.x, 0x7632));
-    dst[1] = make_uint4(__byte_perm(a.y, b.y, 0x5410), __byte_perm(c.y, d.y, 0x5410), __byte_perm(a.y, b.y, 0x7632), __byte_perm(c.y, d.y, 0x7632));
+    const uint16_t* la = luts + (size_t)(ty1 * p.tx + tx1) * kBins16;
+    const uint16_t* lb = luts + (size_t)(ty1 * p.tx + tx2) * kBins16;
+    const uint16_t* lc = luts + (size_t)(ty2 * p.tx + tx1) * kBins16;
+    const uint16_t* ld = luts + (size_t)(ty2 * p.tx + tx2) * kBins16;
+    uint2* dst = p.cells + ((size_t)f * (p.ty + 1) * ncx + cell) * kBins16 + (size_t)v4 * 4;
+    if (4 * v4 + 4 <= (kBins16 >> z)) {
+        const uint2 a = reinterpret_cast<const uint2*>(la)[v4], b = reinterpret_cast<const uint2*>(lb)[v4];
+        const uint2 c = reinterpret_cast<const uint2*>(lc)[v4], d = reinterpret_cast<const uint2*>(ld)[v4];
+        // 0x5410: low halves of the two words packed, 0x7632: high halves
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(__byte_perm(a.x, b.x, 0x5410), __byte_perm(c.x, d.x, 0x5410),
+                                                      __byte_perm(a.x, b.x, 0x7632), __byte_perm(c.x, d.x, 0x7632));
+        reinterpret_cast<uint4*>(dst)[1] = make_uint4(__byte_perm(a.y, b.y, 0x5410), __byte_perm(c.y, d.y, 0x5410),
+                                                      __byte_perm(a.y, b.y, 0x7632), __byte_perm(c.y, d.y, 0x7632));
+    } else {
+        for (int k = 4 * v4; k < (kBins16 >> z); ++k)   // fewer than four entries in all (z > 14)
+            dst[k - 4 * v4] = make_uint2((uint32_t)la[k] | ((uint32_t)lb[k] << 16), (uint32_t)lc[k] | ((uint32_t)ld[k] << 16));
+    }
 }
 
 constexpr int kC16RowsPerCta = 8;
 
-// grid (ceil(w / 256), ceil(h / 8), planes): a thread owns one column of 8 rows, so the x weights are computed once.
+// grid (ceil(w / 256), ceil(h / 8), planes): a thread owns one column of 8 rows, so the x weights are computed once; the
+// weights and cell rows of the 8 rows are shared by the CTA.
 __global__ void __launch_bounds__(kC16Threads) clahe16_interp_kernel(const Clahe16Params p) {
+    __shared__ float2 s_yw[kC16RowsPerCta];   // (ya1, ya)
+    __shared__ uint32_t s_row[kC16RowsPerCta];  // first entry of the row's cell row
     const int ncx = p.tx + 1;
     const int f = blockIdx.z;
+    const int y0 = blockIdx.y * kC16RowsPerCta, y1 = min(y0 + kC16RowsPerCta, p.h);
+    if (threadIdx.x < kC16RowsPerCta) {
+        const int y = y0 + threadIdx.x;
+        float ya, ya1;
+        axis_weight(y, p.inv_th, ya, ya1);
+        const int cy = (int)floorf(__fsub_rn(__fmul_rn((float)y, p.inv_th), 0.5f)) + 1;   // 0 .. ty
+        s_yw[threadIdx.x] = make_float2(ya1, ya);
+        s_row[threadIdx.x] = (uint32_t)(min(cy, p.ty) * ncx) * (uint32_t)kBins16;
+    }
+    __syncthreads();
     const int x = blockIdx.x * kC16Threads + threadIdx.x;
     if (x >= p.w) return;
+    const int z = c16_zero_bits(__ldg(p.ormask + f));
     float xa, xa1;
     axis_weight(x, p.inv_tw, xa, xa1);
     const int cx = (int)floorf(__fsub_rn(__fmul_rn((float)x, p.inv_tw), 0.5f)) + 1;   // 0 .. tx
-    const uint2* cells = p.cells + (size_t)f * (p.ty + 1) * ncx * kBins16;
-    const int y0 = blockIdx.y * kC16RowsPerCta, y1 = min(y0 + kC16RowsPerCta, p.h);
-    const uint16_t* src = p.in + (unsigned long long)f * p.pitch + x;
-    uint16_t* dst = p.out + (unsigned long long)f * p.pitch + x;
+    const uint2* cells = p.cells + (size_t)f * (p.ty + 1) * ncx * kBins16 + (size_t)cx * kBins16;
+    const uint16_t* src = p.in + (unsigned long long)f * p.pitch + (size_t)y0 * p.stride + x;
+    uint16_t* dst = p.out + (unsigned long long)f * p.pitch + (size_t)y0 * p.stride + x;
     uint32_t v[kC16RowsPerCta];
 #pragma unroll
-    for (int k = 0; k < kC16RowsPerCta; ++k) v[k] = y0 + k < y1 ? src[(size_t)(y0 + k) * p.stride] : 0u;
+    for (int k = 0; k < kC16RowsPerCta; ++k) v[k] = y0 + k < y1 ? src[(size_t)k * p.stride] : 0u;
+    uint2 e[kC16RowsPerCta];
+#pragma unroll
+    for (int k = 0; k < kC16RowsPerCta; ++k) e[k] = __ldg(cells + (s_row[k] + (v[k] >> z)));
 #pragma unroll
     for (int k = 0; k < kC16RowsPerCta; ++k) {
-        const int y = y0 + k;
-        if (y < y1) {
-            float ya, ya1;
-            axis_weight(y, p.inv_th, ya, ya1);
-            const int cy = (int)floorf(__fsub_rn(__fmul_rn((float)y, p.inv_th), 0.5f)) + 1;   // 0 .. ty
-            const uint2 e = __ldg(cells + (size_t)(cy * ncx + cx) * kBins16 + v[k]);
-            const float l11 = (float)(e.x & 0xffffu), l12 = (float)(e.x >> 16);
-            const float l21 = (float)(e.y & 0xffffu), l22 = (float)(e.y >> 16);
+        if (y0 + k < y1) {
+            const float2 yw = s_yw[k];
+            const float l11 = (float)(e[k].x & 0xffffu), l12 = (float)(e[k].x >> 16);
+            const float l21 = (float)(e[k].y & 0xffffu), l22 = (float)(e[k].y >> 16);
             const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
             const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-            const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-            dst[(size_t)y * p.stride] = (uint16_t)min(max(__float2int_rn(res), 0), 65535);
+            const float res = __fadd_rn(__fmul_rn(top, yw.x), __fmul_rn(bot, yw.y));
+            dst[(size_t)k * p.stride] = (uint16_t)min(max(__float2int_rn(res), 0), 65535);
         }
     }
 }

@@ -71,6 +71,7 @@ struct Workspace {
     DevBuf hist16;    // clahe16: [planes][tiles][65536] u32, kept zero between launches
     DevBuf luts16;    // clahe16: [planes][tiles][65536] u16
     DevBuf cells16;   // clahe16: [planes][cells][65536] four u16 per value
+    DevBuf ormask16;  // clahe16: [planes] OR of the pixel values
     int frames_cap = 0;
     // cached CLAHE geometry
     int gw = 0, gh = 0, gtx = 0, gty = 0, nxc = 0, nyc = 0;
@@ -249,7 +250,7 @@ void host_release(HostBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap
 
 void ws_release(Workspace& w) {
     dev_release(w.hist); dev_release(w.counters); dev_release(w.misc); dev_release(w.luts); dev_release(w.cells);
-    dev_release(w.luma); dev_release(w.hist16); dev_release(w.luts16); dev_release(w.cells16);
+    dev_release(w.luma); dev_release(w.hist16); dev_release(w.luts16); dev_release(w.cells16); dev_release(w.ormask16);
     w.frames_cap = 0; w.gw = w.gh = w.gtx = w.gty = 0;
 }
 
@@ -1225,22 +1226,27 @@ static int launch_clahe16(nv12eq_ctx* ctx, Workspace& ws, const uint16_t* d_in, 
     p.lut_scale = 65535.0f / (float)area;
     p.inv_tw = 1.0f / (float)p.tw; p.inv_th = 1.0f / (float)p.th;
     if (p.tw > kC16StripPixels) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "16-bit tile rows of %d pixels are not supported", p.tw);
-    // planes per pass: one plane's histograms (256 KB per tile), LUTs (128 KB per tile) and cell tables (512 KB per cell)
-    // should stay L2-resident between the kernels, so a pass takes few planes -- just enough tiles to fill the GPU
+    // Planes per pass.  Histograms (256 KB per tile) and LUTs (128 KB per tile) of a pass should stay L2-resident between the
+    // histogram and the LUT kernel: up to 256 tiles per pass, which also fills the GPU with LUT clusters.  The cell tables
+    // (512 KB per cell) are gathered from at random by the blend and must not spill to HBM: about 64 tiles' worth per pass.
     const int cells = (tx + 1) * (ty + 1);
-    const int group = std::max(1, std::min(n, 64 / T));
+    const int group = std::max(1, std::min(n, 256 / T));
+    const int cgroup = std::max(1, std::min(group, 64 / T));
     int rc = ensure_attrs(ctx);
     if (rc) return rc;
     rc = dev_reserve(ctx, ws.hist16, (size_t)group * T * kBins16 * sizeof(uint32_t), true);
     if (rc) return rc;
     if ((rc = dev_reserve(ctx, ws.luts16, (size_t)group * T * kBins16 * sizeof(uint16_t), false))) return rc;
-    if ((rc = dev_reserve(ctx, ws.cells16, (size_t)group * cells * kBins16 * sizeof(uint2), false))) return rc;
+    if ((rc = dev_reserve(ctx, ws.cells16, (size_t)cgroup * cells * kBins16 * sizeof(uint2), false))) return rc;
+    if ((rc = dev_reserve(ctx, ws.ormask16, (size_t)group * sizeof(uint32_t), false))) return rc;
     p.hist = reinterpret_cast<uint32_t*>(ws.hist16.p);
-    p.luts = reinterpret_cast<uint16_t*>(ws.luts16.p);
     p.cells = reinterpret_cast<uint2*>(ws.cells16.p);
+    uint32_t* const ormask = reinterpret_cast<uint32_t*>(ws.ormask16.p);
+    uint16_t* const luts = reinterpret_cast<uint16_t*>(ws.luts16.p);
     for (int g0 = 0; g0 < n; g0 += group) {
         const int ng = std::min(group, n - g0);
-        p.in = d_in + (size_t)g0 * pitch; p.out = d_out + (size_t)g0 * pitch; p.n_planes = ng;
+        p.in = d_in + (size_t)g0 * pitch; p.out = d_out + (size_t)g0 * pitch; p.n_planes = ng; p.luts = luts; p.ormask = ormask;
+        CK(ctx, cudaMemsetAsync(ormask, 0, (size_t)ng * sizeof(uint32_t), st));
         // strips: short enough for 16-bit counters; one CTA runs per SM, so as many strips as fit into one wave (every
         // further strip costs another zeroing and flush of the 128 KB counter table)
         const int max_rows = std::max(1, kC16StripPixels / p.tw);
@@ -1249,9 +1255,16 @@ static int launch_clahe16(nv12eq_ctx* ctx, Workspace& ws, const uint16_t* d_in, 
         p.strips = (p.th + p.rows_strip - 1) / p.rows_strip;
         clahe16_hist_kernel<<<dim3(p.strips, T, ng), kC16HistThreads, kC16HistSmemBytes, st>>>(p);
         clahe16_lut_kernel<<<dim3(kC16Parts, T, ng), kC16LutThreads, 0, st>>>(p);
-        clahe16_cell_table_kernel<<<dim3(kBins16 / (kC16Threads * 4), cells, ng), kC16Threads, 0, st>>>(p);
-        clahe16_interp_kernel<<<dim3((w + kC16Threads - 1) / kC16Threads, (h + kC16RowsPerCta - 1) / kC16RowsPerCta, ng), kC16Threads, 0, st>>>(p);
-        ctx->ctr.kernel_launches += 4;
+        ctx->ctr.kernel_launches += 2;
+        for (int c0 = 0; c0 < ng; c0 += cgroup) {
+            const int nc = std::min(cgroup, ng - c0);
+            Clahe16Params q = p;
+            q.in = p.in + (size_t)c0 * pitch; q.out = p.out + (size_t)c0 * pitch; q.n_planes = nc;
+            q.luts = luts + (size_t)c0 * T * kBins16; q.ormask = ormask + c0;
+            clahe16_cell_table_kernel<<<dim3(kBins16 / (kC16Threads * 4), cells, nc), kC16Threads, 0, st>>>(q);
+            clahe16_interp_kernel<<<dim3((w + kC16Threads - 1) / kC16Threads, (h + kC16RowsPerCta - 1) / kC16RowsPerCta, nc), kC16Threads, 0, st>>>(q);
+            ctx->ctr.kernel_launches += 2;
+        }
         CK(ctx, cudaGetLastError());
     }
     return NV12EQ_OK;

@@ -221,3 +221,35 @@ def test_gpu_clahe16_device_batch(nv, oracle):
         got = d_out.cpu().numpy().view(np.uint16)
         for k in (0, 7, 15, 16, 19):
             assert np.array_equal(got[k], oracle.c_clahe16(planes[k], 2.0, 8, 8)), k
+
+
+@pytest.mark.gpu
+def test_gpu_clahe16_bit_depths_in_one_batch(nv, oracle):
+    """The cell tables are indexed at v >> z, z = number of low bits that are zero in every pixel of the plane (found on the
+    fly, per plane).  One batch mixes planes of every kind: 10-, 12-, 14- and 16-bit content, a plane with a single odd
+    pixel (z collapses to 0), constant planes (z = 12, and all-zero: z = 16) -- each must equal OpenCV's 65536-bin result."""
+    import torch
+    W, H = 200, 120
+    rng = np.random.default_rng(77)
+    planes = [
+        (rng.integers(0, 1024, (H, W)) << 6).astype(np.uint16),
+        (rng.integers(0, 4096, (H, W)) << 4).astype(np.uint16),
+        (rng.integers(0, 16384, (H, W)) << 2).astype(np.uint16),
+        rng.integers(0, 65536, (H, W)).astype(np.uint16),
+        (rng.integers(0, 1024, (H, W)) << 6).astype(np.uint16),
+        np.full((H, W), 4096, np.uint16),
+        np.zeros((H, W), np.uint16),
+        (rng.integers(0, 2, (H, W)) << 15).astype(np.uint16),
+    ]
+    planes[4][H - 1, W - 1] |= 1                      # one odd pixel in the last corner
+    batch = np.stack(planes)
+    n = len(planes)
+    with nv.Context(0, W, H, 1) as ctx:
+        d_in = torch.from_numpy(batch.view(np.int16)).cuda()
+        for clip, tiles in ((2.0, (8, 8)), (40.0, (3, 5)), (0.0, (1, 1))):
+            d_out = torch.zeros_like(d_in)
+            ctx.clahe16_device(d_in, d_out, n, W * H, W, H, clip, tiles, stream=torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy().view(np.uint16)
+            for k in range(n):
+                assert np.array_equal(got[k], oracle.c_clahe16(planes[k], clip, tiles[0], tiles[1])), (k, clip, tiles)
