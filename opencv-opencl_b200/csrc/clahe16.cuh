@@ -53,7 +53,7 @@ struct Clahe16Params {
 };
 
 // word of the packed shared histogram that holds bins 2*w and 2*w + 1 (an involution: it is its own inverse)
-__device__ __forceinline__ uint32_t c16_swizzle(uint32_t w) { return w ^ ((w >> 5) & 31u); }
+__device__ __forceinline__ uint32_t c16_swizzle(uint32_t w) { return w ^ ((w >> 5) & 31u) ^ ((w >> 10) & 31u); }
 __device__ __forceinline__ void c16_count(uint32_t* cnt, uint32_t v) {
     atomicAdd(cnt + c16_swizzle(v >> 1), (v & 1u) ? 0x10000u : 1u);
 }
@@ -196,6 +196,10 @@ __global__ void __cluster_dims__(kC16Parts, 1, 1) __launch_bounds__(kC16LutThrea
     const int z = c16_zero_bits(__ldg(p.ormask + f));
     const int nb = kBins16 >> z;
     constexpr int B = kC16BinsPerThread;
+    // At most 8192 compact bins (13-bit content or less, e.g. P010): part 0 owns them all and runs on its own; the
+    // decision is the same in every CTA of the cluster, so nobody waits for the CTAs that leave here.
+    const bool solo = nb <= kC16PartBins;
+    if (solo && part > 0) return;
     const int k0 = part * kC16PartBins + threadIdx.x * B;   // first compact bin of this thread
     uint32_t* hist = p.hist + ((size_t)f * T + t) * kBins16;
     uint16_t* lut = p.luts + ((size_t)f * T + t) * kBins16;
@@ -218,10 +222,12 @@ __global__ void __cluster_dims__(kC16Parts, 1, 1) __launch_bounds__(kC16LutThrea
     }
     const int2 mine = block_sum2(kept, excess, s_warp);
     if (threadIdx.x == 0) s_part = mine;
-    cluster.sync();   // release/acquire on s_part; no global store is pending yet, so the fence is cheap
+    if (!solo) cluster.sync();   // release/acquire on s_part; no global store is pending yet, so the fence is cheap
+    else __syncthreads();
     if (warp == 0) {
         int2 v = make_int2(0, 0);
-        if (lane < kC16Parts) v = *cluster.map_shared_rank(&s_part, lane);
+        if (solo) { if (lane == 0) v = s_part; }
+        else if (lane < kC16Parts) v = *cluster.map_shared_rank(&s_part, lane);
         int clipped = v.y;
         int before = lane < part ? v.x : 0;
 #pragma unroll
@@ -236,7 +242,7 @@ __global__ void __cluster_dims__(kC16Parts, 1, 1) __launch_bounds__(kC16LutThrea
     __syncthreads();
     // the remote reads of this CTA are done: arrive now, wait at the very end (s_part must outlive the other CTAs' reads);
     // relaxed, because nothing written after this point is read inside the cluster
-    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    if (!solo) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     // histogram back to zero, ready for the next launch
     if (z == 0) {
 #pragma unroll
@@ -271,18 +277,17 @@ __global__ void __cluster_dims__(kC16Parts, 1, 1) __launch_bounds__(kC16LutThrea
                 if (k0 + j8 + j < nb) lut[k0 + j8 + j] = (uint16_t)o[j];
         }
     }
-    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    if (!solo) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
 }
 
-// grid (65536 / 1024, cells, planes), 256 threads x 4 table entries: the four tile LUTs a cell blends, interleaved per
+// grid (8, cells, planes), 256 threads x 4 table entries per round: the four tile LUTs a cell blends, interleaved per
 // value.  Cell (cy, cx) lies between tile rows cy-1, cy and tile columns cx-1, cx (clamped to the grid).  Like the tile
 // LUTs the table is compact: entry k holds value k << z (see c16_zero_bits), entries past 65536 >> z do not exist.
 __global__ void __launch_bounds__(kC16Threads) clahe16_cell_table_kernel(const Clahe16Params p) {
     const int T = p.tx * p.ty, ncx = p.tx + 1;
     const int cell = blockIdx.y, f = blockIdx.z;
     const int z = c16_zero_bits(__ldg(p.ormask + f));
-    const int v4 = blockIdx.x * kC16Threads + threadIdx.x;   // entries 4*v4 .. 4*v4+3
-    if (4 * v4 >= (kBins16 >> z)) return;
+    const int nb = kBins16 >> z;
     const int cy = cell / ncx, cx = cell - cy * ncx;
     const int ty1 = max(cy - 1, 0), ty2 = min(cy, p.ty - 1), tx1 = max(cx - 1, 0), tx2 = min(cx, p.tx - 1);
     const uint16_t* luts = p.luts + (size_t)f * T * kBins16;
@@ -290,25 +295,61 @@ __global__ void __launch_bounds__(kC16Threads) clahe16_cell_table_kernel(const C
     const uint16_t* lb = luts + (size_t)(ty1 * p.tx + tx2) * kBins16;
     const uint16_t* lc = luts + (size_t)(ty2 * p.tx + tx1) * kBins16;
     const uint16_t* ld = luts + (size_t)(ty2 * p.tx + tx2) * kBins16;
-    uint2* dst = p.cells + ((size_t)f * (p.ty + 1) * ncx + cell) * kBins16 + (size_t)v4 * 4;
-    if (4 * v4 + 4 <= (kBins16 >> z)) {
-        const uint2 a = reinterpret_cast<const uint2*>(la)[v4], b = reinterpret_cast<const uint2*>(lb)[v4];
-        const uint2 c = reinterpret_cast<const uint2*>(lc)[v4], d = reinterpret_cast<const uint2*>(ld)[v4];
-        // 0x5410: low halves of the two words packed, 0x7632: high halves
-        reinterpret_cast<uint4*>(dst)[0] = make_uint4(__byte_perm(a.x, b.x, 0x5410), __byte_perm(c.x, d.x, 0x5410),
-                                                      __byte_perm(a.x, b.x, 0x7632), __byte_perm(c.x, d.x, 0x7632));
-        reinterpret_cast<uint4*>(dst)[1] = make_uint4(__byte_perm(a.y, b.y, 0x5410), __byte_perm(c.y, d.y, 0x5410),
-                                                      __byte_perm(a.y, b.y, 0x7632), __byte_perm(c.y, d.y, 0x7632));
-    } else {
-        for (int k = 4 * v4; k < (kBins16 >> z); ++k)   // fewer than four entries in all (z > 14)
-            dst[k - 4 * v4] = make_uint2((uint32_t)la[k] | ((uint32_t)lb[k] << 16), (uint32_t)lc[k] | ((uint32_t)ld[k] << 16));
+    uint2* table = p.cells + ((size_t)f * (p.ty + 1) * ncx + cell) * kBins16;
+    for (int v4 = blockIdx.x * kC16Threads + threadIdx.x; 4 * v4 < nb; v4 += gridDim.x * kC16Threads) {   // entries 4*v4 .. 4*v4+3
+        uint2* dst = table + (size_t)v4 * 4;
+        if (4 * v4 + 4 <= nb) {
+            const uint2 a = reinterpret_cast<const uint2*>(la)[v4], b = reinterpret_cast<const uint2*>(lb)[v4];
+            const uint2 c = reinterpret_cast<const uint2*>(lc)[v4], d = reinterpret_cast<const uint2*>(ld)[v4];
+            // 0x5410: low halves of the two words packed, 0x7632: high halves
+            reinterpret_cast<uint4*>(dst)[0] = make_uint4(__byte_perm(a.x, b.x, 0x5410), __byte_perm(c.x, d.x, 0x5410),
+                                                          __byte_perm(a.x, b.x, 0x7632), __byte_perm(c.x, d.x, 0x7632));
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(__byte_perm(a.y, b.y, 0x5410), __byte_perm(c.y, d.y, 0x5410),
+                                                          __byte_perm(a.y, b.y, 0x7632), __byte_perm(c.y, d.y, 0x7632));
+        } else {
+            for (int k = 4 * v4; k < nb; ++k)   // fewer than four entries in all (z > 14)
+                dst[k - 4 * v4] = make_uint2((uint32_t)la[k] | ((uint32_t)lb[k] << 16), (uint32_t)lc[k] | ((uint32_t)ld[k] << 16));
+        }
     }
 }
 
-constexpr int kC16RowsPerCta = 8;
+constexpr int kC16RowsPerCta = 16;   // rows per CTA of the blend kernel, in batches of kC16RowBatch per thread
+constexpr int kC16RowBatch = 8;
 
-// grid (ceil(w / 256), ceil(h / 8), planes): a thread owns one column of 8 rows, so the x weights are computed once; the
-// weights and cell rows of the 8 rows are shared by the CTA.
+// One column of up to 8 rows: all pixel loads first, then all table gathers, then the blends.  FULL: all 8 rows exist
+// (no predicates in the unrolled code).
+template <bool FULL>
+__device__ __forceinline__ void c16_blend_rows(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, const uint2* __restrict__ cells,
+                                               uint32_t stride, int nrows, int z, float xa, float xa1, const float2* s_yw,
+                                               const uint32_t* s_row) {
+    uint32_t v[kC16RowBatch];
+#pragma unroll
+    for (int k = 0; k < kC16RowBatch; ++k) v[k] = (FULL || k < nrows) ? src[(uint32_t)k * stride] : 0u;
+    uint2 e[kC16RowBatch];
+#pragma unroll
+    for (int k = 0; k < kC16RowBatch; ++k) e[k] = __ldg(cells + (s_row[k] + (v[k] >> z)));
+#pragma unroll
+    for (int k = 0; k < kC16RowBatch; ++k) {
+        if (FULL || k < nrows) {
+            const float2 yw = s_yw[k];
+            // u16 -> float without the conversion pipe: 0x4B00xxxx is 2^23 + x exactly
+            const float l11 = __fsub_rn(__uint_as_float(__byte_perm(e[k].x, 0x4B000000u, 0x7610)), 8388608.0f);
+            const float l12 = __fsub_rn(__uint_as_float(__byte_perm(e[k].x, 0x4B000000u, 0x7632)), 8388608.0f);
+            const float l21 = __fsub_rn(__uint_as_float(__byte_perm(e[k].y, 0x4B000000u, 0x7610)), 8388608.0f);
+            const float l22 = __fsub_rn(__uint_as_float(__byte_perm(e[k].y, 0x4B000000u, 0x7632)), 8388608.0f);
+            const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+            const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+            const float res = __fadd_rn(__fmul_rn(top, yw.x), __fmul_rn(bot, yw.y));
+            // 0 <= res < 65535.5 (a blend of values in [0, 65535] with weights in [0, 1] that sum to 1 up to rounding), so
+            // adding 1.5 * 2^23 performs cvRound's round-half-to-even and leaves the integer in the low 16 mantissa bits;
+            // saturate_cast is the identity
+            dst[(uint32_t)k * stride] = (uint16_t)__float_as_uint(__fadd_rn(res, 12582912.0f));
+        }
+    }
+}
+
+// grid (ceil(w / 256), ceil(h / 16), planes): a thread owns one column of 16 rows, so the x weights are computed once; the
+// weights and cell rows of the 16 rows are shared by the CTA.
 __global__ void __launch_bounds__(kC16Threads) clahe16_interp_kernel(const Clahe16Params p) {
     __shared__ float2 s_yw[kC16RowsPerCta];   // (ya1, ya)
     __shared__ uint32_t s_row[kC16RowsPerCta];  // first entry of the row's cell row
@@ -333,23 +374,12 @@ __global__ void __launch_bounds__(kC16Threads) clahe16_interp_kernel(const Clahe
     const uint2* cells = p.cells + (size_t)f * (p.ty + 1) * ncx * kBins16 + (size_t)cx * kBins16;
     const uint16_t* src = p.in + (unsigned long long)f * p.pitch + (size_t)y0 * p.stride + x;
     uint16_t* dst = p.out + (unsigned long long)f * p.pitch + (size_t)y0 * p.stride + x;
-    uint32_t v[kC16RowsPerCta];
+    const bool full = y0 + kC16RowsPerCta <= p.h;
 #pragma unroll
-    for (int k = 0; k < kC16RowsPerCta; ++k) v[k] = y0 + k < y1 ? src[(size_t)k * p.stride] : 0u;
-    uint2 e[kC16RowsPerCta];
-#pragma unroll
-    for (int k = 0; k < kC16RowsPerCta; ++k) e[k] = __ldg(cells + (s_row[k] + (v[k] >> z)));
-#pragma unroll
-    for (int k = 0; k < kC16RowsPerCta; ++k) {
-        if (y0 + k < y1) {
-            const float2 yw = s_yw[k];
-            const float l11 = (float)(e[k].x & 0xffffu), l12 = (float)(e[k].x >> 16);
-            const float l21 = (float)(e[k].y & 0xffffu), l22 = (float)(e[k].y >> 16);
-            const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
-            const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-            const float res = __fadd_rn(__fmul_rn(top, yw.x), __fmul_rn(bot, yw.y));
-            dst[(size_t)k * p.stride] = (uint16_t)min(max(__float2int_rn(res), 0), 65535);
-        }
+    for (int b = 0; b < kC16RowsPerCta; b += kC16RowBatch) {
+        const size_t off = (size_t)b * p.stride;
+        if (full) c16_blend_rows<true>(src + off, dst + off, cells, (uint32_t)p.stride, kC16RowBatch, z, xa, xa1, s_yw + b, s_row + b);
+        else if (y0 + b < y1) c16_blend_rows<false>(src + off, dst + off, cells, (uint32_t)p.stride, y1 - y0 - b, z, xa, xa1, s_yw + b, s_row + b);
     }
 }
 

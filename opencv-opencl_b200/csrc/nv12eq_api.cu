@@ -1261,7 +1261,7 @@ static int launch_clahe16(nv12eq_ctx* ctx, Workspace& ws, const uint16_t* d_in, 
             Clahe16Params q = p;
             q.in = p.in + (size_t)c0 * pitch; q.out = p.out + (size_t)c0 * pitch; q.n_planes = nc;
             q.luts = luts + (size_t)c0 * T * kBins16; q.ormask = ormask + c0;
-            clahe16_cell_table_kernel<<<dim3(kBins16 / (kC16Threads * 4), cells, nc), kC16Threads, 0, st>>>(q);
+            clahe16_cell_table_kernel<<<dim3(8, cells, nc), kC16Threads, 0, st>>>(q);
             clahe16_interp_kernel<<<dim3((w + kC16Threads - 1) / kC16Threads, (h + kC16RowsPerCta - 1) / kC16RowsPerCta, nc), kC16Threads, 0, st>>>(q);
             ctx->ctr.kernel_launches += 2;
         }
