@@ -55,7 +55,7 @@ struct Clahe16Params {
 // word of the packed shared histogram that holds bins 2*w and 2*w + 1 (an involution: it is its own inverse)
 __device__ __forceinline__ uint32_t c16_swizzle(uint32_t w) { return w ^ ((w >> 5) & 31u) ^ ((w >> 10) & 31u); }
 __device__ __forceinline__ void c16_count(uint32_t* cnt, uint32_t v) {
-    atomicAdd(cnt + c16_swizzle(v >> 1), (v & 1u) ? 0x10000u : 1u);
+    atomicAdd(cnt + c16_swizzle(v >> 1), (v & 1u) * 0xffffu + 1u);   // +1 in the low or in the high half
 }
 __device__ __forceinline__ void c16_count2(uint32_t* cnt, uint32_t w) {
     c16_count(cnt, w & 0xffffu);
@@ -87,19 +87,26 @@ __global__ void __launch_bounds__(kC16HistThreads, 1) clahe16_hist_kernel(const 
     const bool vec = x0 + p.tw <= p.w && (p.tw & 7) == 0 && (p.stride & 7) == 0 && (((uintptr_t)src + 2 * (uintptr_t)x0) & 15) == 0;
     if (vec) {
         const int vpr = p.tw >> 3, n = (r1 - r0) * vpr;
-        auto load = [&](int i) {
-            const int r = i / vpr, c = i - r * vpr;
-            return __ldg(reinterpret_cast<const uint4*>(src + (size_t)reflect101(y0 + r0 + r, p.h) * p.stride + x0) + c);
+        // vector i of the strip is vector c of row r; the pair advances by one CTA stride without a division
+        const int dr = kC16HistThreads / vpr, dc = kC16HistThreads - dr * vpr;
+        int r = (int)threadIdx.x / vpr, c = (int)threadIdx.x - r * vpr;
+        const uint16_t* tile = src + x0;
+        auto load = [&]() {
+            const int y = y0 + r0 + r;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(tile + (size_t)(y < p.h ? y : reflect101(y, p.h)) * p.stride) + c);
+            c += dc; r += dr;
+            if (c >= vpr) { c -= vpr; ++r; }
+            return q;
         };
         // two vectors in flight per thread: the loads of the next round overlap the shared atomics of this one
         int i = threadIdx.x;
         uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-        if (i < n) q0 = load(i);
-        if (i + kC16HistThreads < n) q1 = load(i + kC16HistThreads);
+        if (i < n) q0 = load();
+        if (i + kC16HistThreads < n) q1 = load();
         while (i < n) {
             const uint4 q = q0;
             q0 = q1;
-            if (i + 2 * kC16HistThreads < n) q1 = load(i + 2 * kC16HistThreads);
+            if (i + 2 * kC16HistThreads < n) q1 = load();
             seen |= q.x | q.y | q.z | q.w;
             c16_count2(cnt, q.x); c16_count2(cnt, q.y); c16_count2(cnt, q.z); c16_count2(cnt, q.w);
             i += kC16HistThreads;
