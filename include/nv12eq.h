@@ -161,7 +161,9 @@ int nv12eq_query(nv12eq_ctx* ctx, int slot);
 
 /* ---- device-resident forms (d_* are device pointers; asynchronous on `cuda_stream`) -------------------- */
 /* cuda_stream is a cudaStream_t passed as void*.  NULL selects the context's own (non-blocking) stream, which
- * nv12eq_sync waits for; to run on the default stream pass cudaStreamLegacy or cudaStreamPerThread explicitly. */
+ * nv12eq_sync waits for; to run on the default stream pass cudaStreamLegacy or cudaStreamPerThread explicitly.
+ * The device forms of one context share a workspace: calls are ordered on their stream, and when consecutive calls use
+ * different streams the later stream is made to wait for the earlier one (use one context per stream for overlap). */
 int nv12eq_equalize_hist_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t frame_pitch,
                                 int width, int height, int stride, int uv_mode, void* cuda_stream);
 int nv12eq_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t frame_pitch,

@@ -192,6 +192,9 @@ struct nv12eq_ctx {
     std::vector<Lane> lanes;
     cudaStream_t own_stream = nullptr;
     Workspace dev_ws;  // for *_device entry points
+    cudaStream_t dev_ws_stream = nullptr;   // stream of the last *_device call: the workspace is ordered on it
+    bool dev_ws_used = false;
+    cudaEvent_t dev_ws_event = nullptr;
     std::string last_error;
     nv12eq_counters ctr{};
     bool attrs_set = false;
@@ -915,6 +918,7 @@ void nv12eq_destroy(nv12eq_ctx* ctx) {
         if (L.stream) cudaStreamDestroy(L.stream);
     }
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
+    if (ctx->dev_ws_event) cudaEventDestroy(ctx->dev_ws_event);
     ws_release(ctx->dev_ws);
     delete ctx->pool;
     delete ctx;
@@ -1023,7 +1027,26 @@ int nv12eq_query(nv12eq_ctx* ctx, int slot) {
 }
 
 // ---- device forms ---------------------------------------------------------------------------------------
-static cudaStream_t pick_stream(nv12eq_ctx* ctx, void* s) { return s ? reinterpret_cast<cudaStream_t>(s) : ctx->own_stream; }
+// All *_device calls of a context share one workspace (ticket counter, histograms, tables).  Calls on the same stream are
+// ordered by the stream; when the caller switches streams the new stream is made to wait for everything the previous one
+// has been given so far, so two streams never run kernels on the workspace at the same time.
+static cudaStream_t pick_stream(nv12eq_ctx* ctx, void* s) {
+    const cudaStream_t st = s ? reinterpret_cast<cudaStream_t>(s) : ctx->own_stream;
+    if (ctx->dev_ws_used && st != ctx->dev_ws_stream) {
+        DeviceGuard guard(ctx->device);
+        bool ordered = false;
+        if (!ctx->dev_ws_event) cudaEventCreateWithFlags(&ctx->dev_ws_event, cudaEventDisableTiming);
+        if (ctx->dev_ws_event && cudaEventRecord(ctx->dev_ws_event, ctx->dev_ws_stream) == cudaSuccess)
+            ordered = cudaStreamWaitEvent(st, ctx->dev_ws_event, 0) == cudaSuccess;
+        if (!ordered) {   // e.g. the previous stream has been destroyed by the caller: its work is complete or will never run
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+        }
+    }
+    ctx->dev_ws_stream = st;
+    ctx->dev_ws_used = true;
+    return st;
+}
 
 int nv12eq_equalize_hist_device(nv12eq_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t frame_pitch, int width,
                                 int height, int stride, int uv_mode, void* cuda_stream) {

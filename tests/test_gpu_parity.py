@@ -439,3 +439,27 @@ def test_color_host_batch(nv, ctx, oracle):
     ctx.color_equalize_batch(pin_in.array.reshape(frames.shape), nv.COLOR_YCRCB, out=pin_out.array.reshape(frames.shape))
     assert np.array_equal(pin_out.array.reshape(frames.shape), want)
     pin_in.free(); pin_out.free()
+
+
+def test_device_calls_alternating_streams(nv, ctx, oracle):
+    """The device forms of one context share a workspace; consecutive calls on different CUDA streams must be ordered by the
+    library (the later stream waits for the earlier one), not race on the ticket counter and the tables."""
+    import torch
+    W, H, n = 640, 360, 24
+    pitch = nv.nv12_frame_bytes(W, H)
+    frames = np.stack([oracle.c_synth_nv12(W, H, 77, k) for k in range(n)])
+    d_in = torch.from_numpy(frames).cuda()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = [(torch.zeros_like(d_in), torch.zeros_like(d_in)) for _ in range(6)]
+    torch.cuda.synchronize()
+    for d_eq, d_cl in outs:
+        ctx.equalize_hist_device(d_in, d_eq, n, pitch, W, H, stream=sa)
+        ctx.clahe_device(d_in, d_cl, n, pitch, W, H, 2.0, (8, 8), stream=sb)
+        ctx.equalize_hist_device(d_in, d_eq, n, pitch, W, H, stream=sb)
+        ctx.clahe_device(d_in, d_cl, n, pitch, W, H, 2.0, (8, 8), stream=sa)
+    torch.cuda.synchronize()
+    want_eq = oracle.c_nv12_batch("equalize", frames, W, H)
+    want_cl = oracle.c_nv12_batch("clahe", frames, W, H, clip=2.0, tx=8, ty=8)
+    for d_eq, d_cl in outs:
+        assert np.array_equal(d_eq.cpu().numpy(), want_eq)
+        assert np.array_equal(d_cl.cpu().numpy(), want_cl)
