@@ -253,3 +253,20 @@ def test_gpu_clahe16_bit_depths_in_one_batch(nv, oracle):
             got = d_out.cpu().numpy().view(np.uint16)
             for k in range(n):
                 assert np.array_equal(got[k], oracle.c_clahe16(planes[k], clip, tiles[0], tiles[1])), (k, clip, tiles)
+
+
+@pytest.mark.gpu
+def test_gpu_clahe16_large_planes_mixed_content(nv, oracle):
+    """Large planes and tiles (the 4K / 1080p regime of the bench) with 10-bit, full-range and 14-bit content in one launch.
+    Odd sizes exercise the padded tiles, the partial row batches and the last column block."""
+    import torch
+    for (W, H, tiles) in ((1920, 1080, (8, 8)), (1366, 770, (4, 3)), (1000, 523, (2, 1)), (2048, 1100, (7, 8))):
+        planes = np.stack([plane16(W, H, "p010", 5), plane16(W, H, "full", 6), plane16(W, H, "p010", 7) >> 2 << 2])
+        with nv.Context(0, W, H, 1) as ctx:
+            d_in = torch.from_numpy(planes.view(np.int16)).cuda()
+            d_out = torch.zeros_like(d_in)
+            ctx.clahe16_device(d_in, d_out, 3, W * H, W, H, 3.0, tiles, stream=torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy().view(np.uint16)
+            for k in range(3):
+                assert np.array_equal(got[k], oracle.c_clahe16(planes[k], 3.0, tiles[0], tiles[1])), (W, H, tiles, k)
