@@ -94,7 +94,7 @@ struct ClaheParams {
     uint32_t* ticket;      // [1] self-cleaned
     uint32_t* status;      // [1]
     unsigned long long* trace;  // optional [items][4] (developer tool)
-    int debug_skip;             // developer tool: bit0 skip tile histogram, bit1 skip cell blend, bit2 skip uv, bit3 skip LUT warp, bit4 skip table build
+    int debug_skip;             // developer tool: bit0 skip tile histogram, bit1 skip cell blend, bit2 skip uv, bit3 skip LUT build, bit4 skip table build
 };
 
 __device__ __forceinline__ int reflect101(int p, int len) {
@@ -157,43 +157,42 @@ __device__ __forceinline__ uint32_t hist256_row_sum(const uint32_t* tab, int bin
     return s;
 }
 
-// One warp: tile histogram (shared, 256 ints) -> clip -> redistribute -> scan -> LUT bytes (global).
-__device__ __forceinline__ void clahe_tile_lut_warp(const uint32_t* __restrict__ s_bins, int clip_limit, float lut_scale,
-                                                    uint8_t* __restrict__ glut, int lane) {
-    int h[8];
+// Tile histogram -> clip -> redistribute -> scan -> LUT bytes (global), by the whole CTA: thread t < 256 owns bin t
+// (count = its histogram value).  The per-bin work (clip, residual test, conversion) runs 256 wide and the two reductions
+// cost one barrier each; a single-warp version kept the other warps of the CTA waiting ~1 us per tile.
+// s_scratch: 2 * kCWarps words.
+__device__ __forceinline__ void clahe_tile_lut_block(uint32_t count, int clip_limit, float lut_scale, uint8_t* __restrict__ glut,
+                                                     uint32_t* s_scratch, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    int h = tid < 256 ? (int)count : 0;
+    if (clip_limit > 0) {   // uniform over the CTA
+        int excess = max(h - clip_limit, 0);
+        h = min(h, clip_limit);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) h[j] = (int)s_bins[lane * 8 + j];
-    if (clip_limit > 0) {
+        for (int d = 16; d >= 1; d >>= 1) excess += __shfl_xor_sync(0xffffffffu, excess, d);
+        if (lane == 0) s_scratch[warp] = (uint32_t)excess;
+        __syncthreads();
         int clipped = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (h[j] > clip_limit) { clipped += h[j] - clip_limit; h[j] = clip_limit; }
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) clipped += __shfl_xor_sync(0xffffffffu, clipped, d);
-        const int batch = clipped / 256;
-        const int residual = clipped - batch * 256;
-        int step = 1;
-        if (residual != 0) step = max(256 / residual, 1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int i = lane * 8 + j;
-            h[j] += batch;
+        for (int w = 0; w < kCWarps; ++w) clipped += (int)s_scratch[w];
+        const int batch = clipped >> 8, residual = clipped & 255;   // clipped >= 0
+        h += batch;
+        if (tid < 256 && residual != 0) {
             // for (i = 0; i < 256 && residual > 0; i += step, residual--) h[i]++
-            if (residual != 0 && (i % step) == 0 && (i / step) < residual) h[j] += 1;
+            const int step = max(256 / residual, 1);
+            const int q = tid / step;
+            if (q * step == tid && q < residual) h += 1;
         }
+        if (tid >= 256) h = 0;
     }
-    int lsum = 0;
+    const uint32_t incl = warp_incl_scan((uint32_t)h, lane);
+    if (lane == 31) s_scratch[kCWarps + warp] = incl;
+    __syncthreads();
+    uint32_t run = incl;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) lsum += h[j];
-    int run = (int)warp_incl_scan((uint32_t)lsum, lane) - lsum;
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        run += h[j];
-        const uint32_t v = round_sat_u8(__fmul_rn(__int2float_rn(run), lut_scale));
-        if (j < 4) lo |= v << (8 * j); else hi |= v << (8 * (j - 4));
-    }
-    reinterpret_cast<uint2*>(glut)[lane] = make_uint2(lo, hi);
+    for (int w = 0; w < kCWarps; ++w)
+        if (w < warp) run += s_scratch[kCWarps + w];
+    if (tid < 256) glut[tid] = (uint8_t)round_sat_u8(__fmul_rn(__int2float_rn((int)run), lut_scale));
 }
 
 // ---- the blend ------------------------------------------------------------------------------------------------
@@ -409,16 +408,14 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                             hist256_byte(src_row[reflect101(x, p.w)], tbase, lane4);
                     }
                 }
-                q.prefetch();  // the row sums and the LUT build (~1 us) hide the ticket round trip
+                q.prefetch();  // the row sums and the LUT build hide the ticket round trip
                 __syncthreads();
-                if (tid < 256) s_bins[tid] = hist256_row_sum(smem_rows, tid);
+                if (!(p.debug_skip & 8))
+                    clahe_tile_lut_block(tid < 256 ? hist256_row_sum(smem_rows, tid) : 0u, p.clip_limit, p.lut_scale,
+                                         p.luts + ((size_t)g * T + r) * 256, s_bins, tid);
+                __threadfence();   // every thread publishes its LUT byte before the tile is counted
                 __syncthreads();
-                if (warp == 0) {
-                    if (!(p.debug_skip & 8)) clahe_tile_lut_warp(s_bins, p.clip_limit, p.lut_scale, p.luts + ((size_t)g * T + r) * 256, lane);
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) atomicAdd(p.tiles_done + g, 1u);
-                }
+                if (tid == 0) atomicAdd(p.tiles_done + g, 1u);
             }
         } else if (f >= 0) {
             const uint8_t* src = p.in + (unsigned long long)f * p.pitch;
