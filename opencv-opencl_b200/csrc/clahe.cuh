@@ -94,6 +94,7 @@ struct ClaheParams {
     uint32_t* ticket;      // [1] self-cleaned
     uint32_t* status;      // [1]
     unsigned long long* trace;  // optional [items][4] (developer tool)
+    uint32_t slot_magic;        // floor(2^32 / items per slot) + 1 if items * items_per_slot < 2^32 (exact division by multiply), else 0
     int debug_skip;             // developer tool: bit0 skip tile histogram, bit1 skip cell blend, bit2 skip uv, bit3 skip LUT build, bit4 skip table build
 };
 
@@ -343,8 +344,9 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
     for (;;) {
         const uint32_t item = q.current();
         if (item >= total_items) break;
-        const int g = (int)(item / (uint32_t)per_slot);
-        const int r = (int)(item % (uint32_t)per_slot);
+        // item = g * per_slot + r; the host supplies floor(2^32 / per_slot) + 1 when that multiplier divides exactly
+        const int g = p.slot_magic ? (int)__umulhi(item, p.slot_magic) : (int)(item / (uint32_t)per_slot);
+        const int r = (int)(item - (uint32_t)g * (uint32_t)per_slot);
         const int f = g - p.lag;
         const ItemTrace tr_{p.trace};
         tr_.mark(item, 0);

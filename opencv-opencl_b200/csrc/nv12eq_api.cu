@@ -505,6 +505,7 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
         p.lag = (int)std::min<long long>(lag, std::max(n - 1, 0));
     }
     const long long items = (long long)(n + p.lag) * per_slot;
+    p.slot_magic = (per_slot > 1 && items * per_slot < (1ll << 32)) ? (uint32_t)((1ull << 32) / (unsigned long long)per_slot) + 1u : 0u;
     if (items >= (1ll << 32)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "too many work items");
     // developer tool: NV12EQ_TRACE=<file> dumps per-item timestamps of this launch (synchronous, slow)
     DevBuf trace_buf;
