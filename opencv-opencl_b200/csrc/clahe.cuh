@@ -98,6 +98,12 @@ struct ClaheParams {
     int debug_skip;             // developer tool: bit0 skip tile histogram, bit1 skip cell blend, bit2 skip uv, bit3 skip LUT build, bit4 skip table build
 };
 
+// n / d for 0 <= n < 65536, 1 <= d <= 65536 in five instructions (an integer division costs ~20): (n + 0.5) / d is never
+// closer than 0.5 / d to an integer, i.e. 2^-17 relative, and the approximate reciprocal is good to 2^-21.
+__device__ __forceinline__ int small_div(int n, int d) {
+    if (n >= 65536) return n / d;
+    return __float2int_rz(__fmul_rn(__fadd_rn(__int2float_rn(n), 0.5f), __fdividef(1.0f, __int2float_rn(d))));
+}
 __device__ __forceinline__ int reflect101(int p, int len) {
     if (len == 1) return 0;
     while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * (len - 1) - p;
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
             if (g < p.n_frames) {
                 // ------------------------- tile item: histogram -> clip -> LUT -------------------------
                 const uint8_t* y = p.in + (unsigned long long)g * p.pitch;
-                const int tyi = r / p.tx, txi = r - tyi * p.tx;
+                const int tyi = small_div(r, p.tx), txi = r - tyi * p.tx;
                 const int x0 = txi * p.tw, y0 = tyi * p.th;
                 const uint64_t keep = l2_policy_evict_last();
                 const bool vec_ok = !(p.debug_skip & 1) && !p.padded && (p.tw & 15) == 0 && (p.stride & 15) == 0 &&
@@ -366,9 +372,9 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 // kTileDepth-1 of its 16-byte row pieces in flight through a private cp.async ring; the first ones are issued
                 // before the table is zeroed so that their latency overlaps the set-up of the item.
                 const int vpr = vec_ok ? (p.tw >> 4) : 1;
-                const int rpp = kCT / vpr;
-                const int tr = tid / vpr, tc = tid - tr * vpr;
-                const int nrows = (vec_ok && tr < rpp && tr < p.th) ? (p.th - tr + rpp - 1) / rpp : 0;
+                const int rpp = small_div(kCT, vpr);
+                const int tr = small_div(tid, vpr), tc = tid - tr * vpr;
+                const int nrows = (vec_ok && tr < rpp && tr < p.th) ? small_div(p.th - tr + rpp - 1, rpp) : 0;
                 const uint8_t* ptr = y + (size_t)(y0 + tr) * p.stride + x0 + tc * 16;
                 const size_t rstep = (size_t)rpp * p.stride;
                 const uint32_t ring0 = rbase + (uint32_t)tid * 16u;
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
             if (r < T + I) {
                 // ------------------------- cell item: blend four tile LUTs -------------------------
                 const int ci = r - T;
-                const int cy = ci / p.nxc, cx = ci - cy * p.nxc;
+                const int cy = small_div(ci, p.nxc), cx = ci - cy * p.nxc;
                 const int4 xc = p.xcells[cx], yc = p.ycells[cy];
                 const int cw = xc.y - xc.x, ch = yc.y - yc.x;  // cell size in pixels (ch <= kMaxCellRows)
                 // Geometry of the fast path: full groups of G = 16 (or 8) pixels, one 16- (8-) byte load / store per thread and
@@ -438,12 +444,12 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 const int G = fast16 ? 16 : 8;
                 const int gpr = (p.debug_skip & 2) ? 0 : (fast16 ? (cw >> 4) : (fast8 ? (cw >> 3) : 0));   // G-pixel groups per row
                 const int xslow = xc.x + gpr * G;                               // first column of the pixel-at-a-time path
-                const int rpp = gpr ? kCT / gpr : 1;
-                const int tr = gpr ? tid / gpr : 0, tc = tid - tr * gpr;
+                const int rpp = gpr ? small_div(kCT, gpr) : 1;
+                const int tr = gpr ? small_div(tid, gpr) : 0, tc = tid - tr * gpr;
                 const bool active = gpr > 0 && tr < rpp && tr < ch;
                 const int xg = xc.x + tc * G;
                 const size_t rstep = (size_t)rpp * p.stride;
-                const int nrows = active ? (ch - tr + rpp - 1) / rpp : 0;   // rows of this thread: tr, tr + rpp, ...
+                const int nrows = active ? small_div(ch - tr + rpp - 1, rpp) : 0;   // rows of this thread: tr, tr + rpp, ...
                 const uint8_t* sp = src + (size_t)(yc.x + tr) * p.stride + xg;
                 uint8_t* dp = dst + (size_t)(yc.x + tr) * p.stride + xg;
                 const uint32_t yw_addr = ywbase + (uint32_t)tr * 8u, yw_step = (uint32_t)rpp * 8u;
