@@ -553,7 +553,8 @@ int launch_color_fused(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint
     const int ctas = ctx->sm_count * 2;
     long long C = (long long)((p.rounds + 255) / 256);  // ~128K pixels (384 KB of BGR) per item
     if ((long long)n * C < 2ll * ctas) C = std::min<long long>((2ll * ctas + n - 1) / n, (long long)((p.rounds + 15) / 16));
-    C = std::max<long long>(1, std::min<long long>(C, 1 << 16));
+    if (ctx->tune_chunks > 0) C = ctx->tune_chunks;
+    C = std::max<long long>(1, std::min<long long>(C, std::min<long long>(1 << 16, (long long)p.rounds)));
     p.chunks = (int)C;
     p.rounds_chunk = (p.rounds + C - 1) / C;
     long long lag = (10ll * ctas + 16 * 2 * C - 1) / (10 * 2 * C);
