@@ -489,10 +489,11 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     if (const char* dbg = getenv("NV12EQ_DEBUG_SKIP")) p.debug_skip = atoi(dbg);
 
     const long long per_slot = (long long)T + (long long)p.nxc * p.nyc + U;
-    // CTAs per SM: with large tiles (4K: 130 K pixels) the cell loop dominates and one CTA fewer per SM, i.e. more
-    // registers per thread (78 instead of 64: no rematerialisation in the blend loop), is 3 % faster; with small tiles
-    // (1080p: 32 K pixels) the per-item phases dominate and the extra CTA wins.
-    const int auto_ctas = ((long long)g.tw * g.th >= 65536 && kClaheCtas > 2) ? kClaheCtas - 1 : kClaheCtas;
+    // CTAs per SM: four 64-register CTAs, or three with 80 registers (no rematerialisation in the blend loop).  Measured on
+    // 4K frames with cool-downs between runs (tools/sweep.py --ctas 4,3,4,3 --cooldown 4): 8x8 grid (130 K-pixel tiles) 7.22 vs
+    // 7.35 us per frame, 6x6 (230 K) 7.05 vs 7.04, 4x4 (518 K) 7.56 vs 7.48 -- the extra CTA wins until the tiles are so
+    // large that the per-item phases no longer matter.
+    const int auto_ctas = ((long long)g.tw * g.th >= 262144 && kClaheCtas > 2) ? kClaheCtas - 1 : kClaheCtas;
     const int per_sm = ctx->tune_ctas > 0 ? std::min(ctx->tune_ctas, kClaheCtas) : auto_ctas;
     {
         // same reasoning as for equalizeHist; tile items run ~1.5x longer than the average item

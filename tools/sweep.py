@@ -2,6 +2,7 @@
 """Time the device-resident kernels over a grid of tuning knobs (GPU box only).  Prints one line per configuration:
 op size frames chunks lag ctas schedule -> ms per batch, us per frame, fraction of the measured HBM roofline."""
 import argparse
+import time
 import itertools
 import json
 import os
@@ -25,6 +26,8 @@ def main():
     ap.add_argument("--ctas", default="0")
     ap.add_argument("--schedules", default="0")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--tiles", type=int, default=8, help="CLAHE tile grid (tiles x tiles)")
+    ap.add_argument("--cooldown", type=float, default=1.0, help="idle seconds before each configuration")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -43,12 +46,13 @@ def main():
         for op in args.ops.split(","):
             for c, l, k, s in itertools.product(*[[int(x) for x in v.split(",")] for v in (args.chunks, args.lags, args.ctas, args.schedules)]):
                 ctx.set_tuning(c, l, k, s)
+                time.sleep(args.cooldown)   # back-to-back configurations push the board into its power cap: later ones would look slower
 
                 def step():
                     if op == "equalize":
                         ctx.equalize_hist_device(d_in, d_out, n, pitch, W, H, stream=st)
                     else:
-                        ctx.clahe_device(d_in, d_out, n, pitch, W, H, 2.0, (8, 8), stream=st)
+                        ctx.clahe_device(d_in, d_out, n, pitch, W, H, 2.0, (args.tiles, args.tiles), stream=st)
                 for _ in range(3):
                     step()
                 torch.cuda.synchronize()
