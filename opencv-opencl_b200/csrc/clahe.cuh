@@ -43,7 +43,7 @@ constexpr int kMaxCellRows = 512;               // rows per interpolation cell (
 //       fill the bubbles of the per-item phases (table build, LUT warp, barriers); measured 8.1 us vs 9.1 us per 4K frame
 //       and 2.6 us vs 3.6 us per 1080p frame against
 //   512 threads x 2 CTAs/SM with 256-byte table rows (one-PRMT addressing, 64 KB table).
-//   The host launches the <kClaheCtas - 1> instantiation (more registers per thread) for tiles of 64 K pixels and more.
+//   The host launches the <kClaheCtas - 1> instantiation (more registers per thread) for tiles of 256 K pixels and more.
 #ifndef NV12EQ_CLAHE_THREADS
 #define NV12EQ_CLAHE_THREADS 256
 #endif
