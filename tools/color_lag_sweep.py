@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Fused colour equalization: time per frame vs the frame lag between the histogram pass and the apply pass and the number
-of chunks per frame (GPU box only).  Usage: color_lag_sweep.py [lags] [chunks]"""
+of chunks per frame (GPU box only).  Usage: color_lag_sweep.py [lags] [chunks] [4k|1080p]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, opencv_opencl_b200 as nv
-W, H, n = 3840, 2160, 128
+W, H = {"4k": (3840, 2160), "1080p": (1920, 1080)}[sys.argv[3] if len(sys.argv) > 3 else "4k"]
+n = 128 if W > 2000 else 256
 pitch = 3 * W * H
 c = nv.Context(0, W, H, 1); st = torch.cuda.current_stream()
 a = torch.empty(n * pitch, dtype=torch.uint8, device="cuda"); b = torch.empty_like(a)
