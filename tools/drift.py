@@ -12,7 +12,9 @@ pitch = nv.nv12_frame_bytes(W, H)
 c = nv.Context(0, W, H, 1); st = torch.cuda.current_stream()
 a = torch.empty(n * pitch, dtype=torch.uint8, device="cuda"); b = torch.empty_like(a)
 c.synth_nv12_device(a, n, pitch, W, H, stream=st)
-f = (lambda: c.equalize_hist_device(a, b, n, pitch, W, H, stream=st)) if op == "equalize" else (lambda: c.clahe_device(a, b, n, pitch, W, H, 2.0, (8, 8), stream=st))
+f = {"equalize": lambda: c.equalize_hist_device(a, b, n, pitch, W, H, stream=st),
+     "clahe": lambda: c.clahe_device(a, b, n, pitch, W, H, 2.0, (8, 8), stream=st),
+     "copy": lambda: b.copy_(a)}[op]   # plain device copy of the same bytes: what does bandwidth alone cost in power?
 pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
 samples, stop = [], threading.Event()
 def sampler():
