@@ -4,20 +4,27 @@
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
 A "step" is one pass of the hot path over one batch of synthetic NV12 frames (SURVEY.md Appendix B generator):
 
-  default workload  = BASELINE.json configs[1]: cv::equalizeHist semantics on a 256-frame 3840x2160 NV12 batch,
+  headline workload = BASELINE.json configs[1]: cv::equalizeHist semantics on a 256-frame 3840x2160 NV12 batch,
                       device resident (2 x 3.19 GB, far larger than the 126 MB L2, so no L2 flush is needed).
   value             = frames/s, inputs already in HBM, timed with CUDA events on the stream the kernel runs on.
   e2e               = frames/s through the host C-ABI call (nv12eq_equalize_hist_batch) with pinned HOST buffers:
                       host->device and device->host copies are inside the timed region.
   roofline          = algorithmic bytes (3*W*H per frame) / kernel time vs the measured HBM peak.
-  cpu_baseline      = the reference's own CPU implementation (OpenCV through cv2, else the C oracle port) on a bounded
-                      sample of the same frames, all host cores, rank 0, N=1 only.
+  cpu_baseline      = the reference's own CPU implementation (OpenCV through cv2, else the C oracle port) on the same
+                      frames, all host cores (plus a one-thread figure), rank 0, N=1 only.
+  workloads         = the other cells of BASELINE.json's metric, each measured like the headline in the same run and
+                      reported with its own value / roofline / parity / clocks record:
+                        clahe_4k, clahe_1080p, equalize_1080p (256-frame NV12 batches) and color_4k (128 BGR frames,
+                        BGR -> YUV -> equalizeHist(Y) -> BGR, configs[4]); clahe_4k also carries an e2e record.
+  sustained         = equalizeHist 4K and CLAHE 4K launched back to back for >= 3 s (the board reaches its power cap after
+                      ~2 s): frames/s over the last second, with clocks and throttle reasons.
 
-`--impl reference` times only that CPU implementation (the reference has no GPU path to run).
+`--impl reference` times only the CPU implementation (the reference has no GPU path to run).
 Multi-GPU: frames are independent units, sharded over ranks with no collective on the data path (weak scaling: every
 rank processes its own 256-frame batch); torch.distributed is used only for the barrier and the max over ranks.
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -28,6 +35,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SIZES = {"4k": (3840, 2160), "1080p": (1920, 1080), "720p": (1280, 720)}
+# the cells of BASELINE.json's metric besides the headline (configs[1]); frames per GPU
+EXTRA_WORKLOADS = [("clahe_4k", "clahe", "4k", 256), ("clahe_1080p", "clahe", "1080p", 256),
+                   ("equalize_1080p", "equalize", "1080p", 256), ("color_4k", "color", "4k", 128)]
 
 
 def parse_args():
@@ -36,11 +46,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--op", default="equalize", choices=["equalize", "clahe"])
+    ap.add_argument("--op", default="equalize", choices=["equalize", "clahe", "color"])
     ap.add_argument("--size", default="4k", choices=sorted(SIZES))
     ap.add_argument("--frames", type=int, default=256, help="frames per batch per GPU")
     ap.add_argument("--clip", type=float, default=2.0)
     ap.add_argument("--tiles", type=int, default=8)
+    ap.add_argument("--workloads", default="auto", choices=["auto", "all", "headline"],
+                    help="auto: the extra metric cells run when the headline is the default workload")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0, help="0 skips the sustained legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the cpu_baseline leg")
@@ -48,7 +61,7 @@ def parse_args():
     ap.add_argument("--lag", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--schedule", type=int, default=0)
-    ap.add_argument("--slots", type=int, default=2, help="host lanes of the context (e2e leg pipelining depth)")
+    ap.add_argument("--slots", type=int, default=0, help="host lanes of the context (e2e leg pipelining depth); 0 = library default")
     return ap.parse_args()
 
 
@@ -59,6 +72,28 @@ def dist_env():
     return rank, world, local
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def kernel_source_sha():
+    """Identity of the kernel sources a profile was taken on (git is not available on the GPU box)."""
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "opencv-opencl_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 # ------------------------------------------------------------------------------------------------------------
 # clocks: sampled DURING the timed region through NVML (same counters nvidia-smi prints)
 # ------------------------------------------------------------------------------------------------------------
@@ -67,10 +102,11 @@ class ClockSampler:
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+    def __init__(self, index, period=0.004):
+        self.samples, self.power, self.reasons, self.max_mhz = [], [], set(), None
         self._stop = threading.Event()
         self._t = None
+        self._period = period
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -85,13 +121,14 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
                 bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
                 for b, name in self.REASONS.items():
                     if bits & b and name != "gpu_idle":
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.004)
+            self._stop.wait(self._period)
 
     def __enter__(self):
         if self._nv:
@@ -108,21 +145,60 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2], "sm_min_mhz": s[0], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s), "power_w_max": max(self.power) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------------------------------
 # CPU legs (checker code: oracle/ is only ever used here as the reported baseline, never on the product path)
 # ------------------------------------------------------------------------------------------------------------
-def cpu_leg(args, W, H, n_frames, steps, warmup):
+def cpu_frames(op, W, H, n):
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 1, 16)) as pool:   # the C generator releases the GIL
+        if op == "color":
+            return np.stack(list(pool.map(lambda k: O.c_synth_bgr(W, H, k), range(n))))
+        return np.stack(list(pool.map(lambda k: O.c_synth_nv12(W, H, 2026, k), range(n))))
+
+
+def cpu_one_thread(args, op, W, H, frame, seconds=1.0):
+    """frames/s of one cv2 thread on one frame (the setNumThreads(1) figure)."""
+    import numpy as np
+    from oracle import oracle as O
+    if not O.have_cv2():
+        return None
+    import cv2
+    cv2.setNumThreads(1)
+    out = np.empty_like(frame)
+    clahe = cv2.createCLAHE(clipLimit=args.clip, tileGridSize=(args.tiles, args.tiles))
+
+    def one():
+        if op == "equalize":
+            O.cv2_nv12_equalize_hist(frame, W, H, out)
+        elif op == "clahe":
+            O.cv2_nv12_clahe(frame, W, H, out, clahe=clahe)
+        else:
+            O.cv2_color_equalize(frame, O.COLOR_YUV)
+    one()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        one()
+        n += 1
+    return n / (time.perf_counter() - t0)
+
+
+def cpu_leg(args, op, W, H, n_frames, steps, warmup):
     """Frames/s of the reference's CPU implementation on `n_frames` synthetic frames per step, all host cores.
     cv2 available -> kind 'reference' (the very OpenCV functions the reference calls, frame-parallel like its
-    --workers threads, nextimprovement.cpp:159-168 / clahevideo.cpp:178-201); otherwise the C oracle port."""
+    --workers threads, nextimprovement.cpp:159-168 / clahevideo.cpp:178-201 / singlecolor.cpp:39-66); otherwise the C
+    oracle port."""
     import numpy as np
     from oracle import oracle as O
     cores = os.cpu_count() or 1
-    frames = np.stack([O.c_synth_nv12(W, H, 2026, k) for k in range(n_frames)])
+    frames = cpu_frames(op, W, H, n_frames)
     out = np.empty_like(frames)
+    opname = {"equalize": "equalizeHist", "clahe": "CLAHE.apply", "color": "cvtColor+equalizeHist+cvtColor"}[op]
     if O.have_cv2():
         import cv2
         from concurrent.futures import ThreadPoolExecutor
@@ -131,26 +207,33 @@ def cpu_leg(args, W, H, n_frames, steps, warmup):
         local = threading.local()
 
         def one(k):
-            if args.op == "equalize":
+            if op == "equalize":
                 O.cv2_nv12_equalize_hist(frames[k], W, H, out[k])
-            else:
+            elif op == "clahe":
                 if not hasattr(local, "clahe"):
                     local.clahe = cv2.createCLAHE(clipLimit=args.clip, tileGridSize=(args.tiles, args.tiles))
                 O.cv2_nv12_clahe(frames[k], W, H, out[k], clahe=local.clahe)
+            else:
+                out[k] = O.cv2_color_equalize(frames[k], O.COLOR_YUV)
 
         pool = ThreadPoolExecutor(max_workers=workers)
 
         def step():
             list(pool.map(one, range(n_frames)))
         kind, used = "reference", workers
-        impl = f"cv2 {cv2.__version__} {'equalizeHist' if args.op == 'equalize' else 'CLAHE.apply'} + UV memcpy, {workers} frame-parallel threads"
+        impl = f"cv2 {cv2.__version__} {opname}{'' if op == 'color' else ' + UV memcpy'}, {workers} frame-parallel threads"
     else:
         used = O.max_threads()
-
-        def step():
-            O.c_nv12_batch(args.op, frames, W, H, clip=args.clip, tx=args.tiles, ty=args.tiles, threads=0, out=out)
+        if op == "color":
+            def step():
+                for k in range(n_frames):
+                    out[k] = O.c_color_equalize(frames[k], O.COLOR_YUV)
+            used = 1
+        else:
+            def step():
+                O.c_nv12_batch(op, frames, W, H, clip=args.clip, tx=args.tiles, ty=args.tiles, threads=0, out=out)
         kind = "port"
-        impl = f"C oracle port (oracle/nv12eq_oracle.c), {used} OpenMP threads"
+        impl = f"C oracle port (oracle/nv12eq_oracle.c), {used} threads"
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -158,44 +241,31 @@ def cpu_leg(args, W, H, n_frames, steps, warmup):
         step()
     dt = time.perf_counter() - t0
     # self-check of the baseline itself against the C oracle on one frame
-    want = (O.c_nv12_equalize_hist(frames[0], W, H) if args.op == "equalize"
-            else O.c_nv12_clahe(frames[0], W, H, args.clip, args.tiles, args.tiles))
+    want = (O.c_nv12_equalize_hist(frames[0], W, H) if op == "equalize"
+            else O.c_nv12_clahe(frames[0], W, H, args.clip, args.tiles, args.tiles) if op == "clahe"
+            else O.c_color_equalize(frames[0], O.COLOR_YUV))
     assert np.array_equal(out[0], want), "CPU baseline disagrees with the oracle"
+    one_thread = cpu_one_thread(args, op, W, H, frames[0])
     return {"value": n_frames * steps / dt, "unit": "frames/s", "cores": used, "host_cores": cores, "kind": kind,
-            "sample": f"{n_frames} synthetic {W}x{H} NV12 frames x {steps} passes ({impl})", "seconds": dt,
-            "ms_per_step": dt / steps * 1e3}
+            "sample": f"{n_frames} synthetic {W}x{H} {'BGR' if op == 'color' else 'NV12'} frames x {steps} passes ({impl})",
+            "seconds": dt, "ms_per_step": dt / steps * 1e3, "one_thread_value": one_thread, "cpu_model": cpu_model()}
 
 
-def calibrate_cpu_frames(args, W, H, target_s, passes):
-    """Pick a frame count so that `passes` passes take about target_s seconds of wall time."""
-    import numpy as np
-    from oracle import oracle as O
-    cores = os.cpu_count() or 1
-    nv12 = O.c_synth_nv12(W, H, 2026, 0)
-    out = np.empty_like(nv12)
-    def one():
-        if O.have_cv2():
-            import cv2
-            cv2.setNumThreads(1)
-            if args.op == "equalize":
-                O.cv2_nv12_equalize_hist(nv12, W, H, out)
-            else:
-                O.cv2_nv12_clahe(nv12, W, H, out, clip=args.clip, tx=args.tiles, ty=args.tiles)
-        else:
-            O.c_nv12_batch(args.op, nv12[None], W, H, clip=args.clip, tx=args.tiles, ty=args.tiles, threads=1)
-    one()                      # first call: imports, page faults, thread pools
-    t0 = time.perf_counter()
-    one()
-    per_frame = max(time.perf_counter() - t0, 1e-4)
-    n = int(target_s / passes / per_frame * min(cores, 16))
-    n = max(min(cores, 128), min(n, 128))
-    calibrate_cpu_frames.per_frame_s = per_frame   # single-thread seconds per frame, for sizing the number of passes
-    return max(4, n)
+def workload_name(op, clip, tiles, frames, W, H):
+    if op == "color":
+        return f"BGR->YUV, equalizeHist(Y), ->BGR on a {frames}-frame {W}x{H} packed BGR batch per GPU (BASELINE configs[4] shape)"
+    name = "equalizeHist" if op == "equalize" else f"CLAHE clip={clip} tiles={tiles}x{tiles}"
+    return f"{name} on a {frames}-frame {W}x{H} NV12 batch per GPU (BASELINE configs[1] shape)"
 
 
-def workload_name(args, W, H):
-    op = "equalizeHist" if args.op == "equalize" else f"CLAHE clip={args.clip} tiles={args.tiles}x{args.tiles}"
-    return f"{op} on a {args.frames}-frame {W}x{H} NV12 batch per GPU (BASELINE configs[1] shape)"
+def config_of(args, W, H):
+    """The same dictionary for both arms: the driver compares them."""
+    n = args.frames
+    frame_bytes = (3 if args.op == "color" else 1.5) * W * H
+    return {"workload": workload_name(args.op, args.clip, args.tiles, n, W, H), "op": args.op, "width": W, "height": H,
+            "frames_per_gpu": n, "uv": "passthrough", "l2": f"inputs {n * frame_bytes / 1e9:.2f} GB per GPU > 126 MB L2, no flush needed",
+            "parallelism": f"frame-sharded x{args.gpus}, no collective",
+            "tuning": {"chunks": args.chunks, "lag": args.lag, "ctas": args.ctas, "schedule": args.schedule}}
 
 
 def run_reference(args):
@@ -203,18 +273,18 @@ def run_reference(args):
     if rank != 0:
         return
     W, H = SIZES[args.size]
-    passes = args.steps + args.warmup
-    n = calibrate_cpu_frames(args, W, H, 60.0, passes)
-    r = cpu_leg(args, W, H, n, args.steps, args.warmup)
+    # every step is one pass over the arm's whole batch (the same frames_per_gpu as the GPU arm), capped by what a few
+    # minutes of CPU time allow: a 4K frame costs ~0.5 ms (equalizeHist) to ~2 ms (CLAHE) per core-pass
+    n = args.frames
+    r = cpu_leg(args, args.op, W, H, n, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "nv12_frames_per_sec", "value": r["value"], "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(args, W, H), "op": args.op, "width": W, "height": H,
-                   "frames_per_step": n, "note": "CPU arm: each step is a bounded sample of the workload"},
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": config_of(args, W, H),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "one_thread_value", "cpu_model", "host_cores")},
         "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "note": "CPU arm: every step is one pass over the same frames_per_gpu batch, on the host cores",
     }
     print(json.dumps(line))
 
@@ -223,6 +293,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import opencv_opencl_b200 as nv12eq
+    from oracle import oracle as O     # checker only: spot checks and the cpu_baseline leg
 
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -233,22 +304,23 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nv12eq.build()
 
-    W, H = SIZES[args.size]
-    n = args.frames
-    pitch = nv12eq.nv12_frame_bytes(W, H)
-    bytes_per_frame_algo = 3 * W * H  # read NV12 once + write NV12 once
-    ctx = nv12eq.Context(device=local, max_width=W, max_height=H, slots=args.slots)
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md): 6650 GB/s"
+    traffic_db, src_sha = {}, kernel_source_sha()
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic_db = json.load(f)
+    except Exception:
+        pass
+
+    W0, H0 = SIZES[args.size]
+    ctx = nv12eq.Context(device=local, max_width=3840 if W0 <= 3840 else W0, max_height=2160 if H0 <= 2160 else H0,
+                         slots=args.slots if args.slots > 0 else nv12eq.default_slots())
     ctx.set_tuning(args.chunks, args.lag, args.ctas, args.schedule)
     stream = torch.cuda.current_stream()
-    d_in = torch.empty(n * pitch, dtype=torch.uint8, device="cuda")
-    d_out = torch.empty_like(d_in)
-    ctx.synth_nv12_device(d_in, n, pitch, W, H, seed=2026, first_frame=rank * n, stream=stream)
-
-    def device_step():
-        if args.op == "equalize":
-            ctx.equalize_hist_device(d_in, d_out, n, pitch, W, H, stream=stream)
-        else:
-            ctx.clahe_device(d_in, d_out, n, pitch, W, H, args.clip, (args.tiles, args.tiles), stream=stream)
 
     def barrier():
         if world > 1:
@@ -262,125 +334,244 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident leg ----
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-    barrier()
-    launches0 = ctx.counters()["kernel_launches"]
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local) as clocks:
-        ev[0].record(stream)
-        for i in range(args.steps):
-            device_step()
-            ev[i + 1].record(stream)
-        barrier()
-    launches = ctx.counters()["kernel_launches"] - launches0
-    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
-    value = world * n * args.steps / (total_ms * 1e-3)
-    kernel_ms = sum(step_ms) / len(step_ms)  # one kernel launch per step: its duration is the step's
-    achieved = n * bytes_per_frame_algo / (kernel_ms * 1e-3) / 1e9
+    def all_ranks_true(flag):
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
 
-    # spot check of the timed output against the oracle (rank 0, one frame) -- a fast wrong kernel is not done
-    parity = None
-    if rank == 0:
-        from oracle import oracle as O
-        k = n - 1
-        frame = d_in[k * pitch:(k + 1) * pitch].cpu().numpy()
-        want = (O.c_nv12_equalize_hist(frame, W, H) if args.op == "equalize"
-                else O.c_nv12_clahe(frame, W, H, args.clip, args.tiles, args.tiles))
-        parity = bool(np.array_equal(d_out[k * pitch:(k + 1) * pitch].cpu().numpy(), want))
+    run_extra = args.workloads == "all" or (args.workloads == "auto" and args.op == "equalize" and args.size == "4k"
+                                            and args.frames == 256 and not (args.chunks or args.lag or args.ctas or args.schedule))
+    specs = [("headline", args.op, args.size, args.frames)] + (EXTRA_WORKLOADS if run_extra else [])
+    max_bytes = max((3 * SIZES[s][0] * SIZES[s][1] if op == "color" else nv12eq.nv12_frame_bytes(*SIZES[s])) * n for _, op, s, n in specs)
+    d_in_all = torch.empty(max_bytes, dtype=torch.uint8, device="cuda")
+    d_out_all = torch.empty_like(d_in_all)
 
-    # ---- end-to-end leg: host C-ABI call with pinned host buffers ----
-    e2e = None
-    if not args.no_e2e:
-        e2e_n = n
-        try:
-            h_in, h_out = nv12eq.PinnedBuffer(e2e_n * pitch), nv12eq.PinnedBuffer(e2e_n * pitch)
-        except nv12eq.Nv12eqError:
-            e2e_n = max(8, n // 8)
-            h_in, h_out = nv12eq.PinnedBuffer(e2e_n * pitch), nv12eq.PinnedBuffer(e2e_n * pitch)
-        torch.cuda.synchronize()
-        # fill the pinned input from the device copy of the same synthetic frames (outside the timed region)
-        import ctypes
-        torch.from_numpy(h_in.array).copy_(d_in[:e2e_n * pitch])
-        torch.cuda.synchronize()
+    class Workload:
+        def __init__(self, key, op, size, n):
+            self.key, self.op, self.size, self.n = key, op, size, n
+            self.W, self.H = SIZES[size]
+            self.pitch = 3 * self.W * self.H if op == "color" else nv12eq.nv12_frame_bytes(self.W, self.H)
+            self.algo_bytes = (6 if op == "color" else 3) * self.W * self.H   # read the frame once + write it once
+            self.d_in, self.d_out = d_in_all[:n * self.pitch], d_out_all[:n * self.pitch]
+            self.kernel = {"equalize": "equalize_kernel", "clahe": "clahe_kernel", "color": "color_equalize_kernel"}[op]
 
-        def host_step():
-            if args.op == "equalize":
-                ctx.equalize_hist_batch(h_in.array, W, H, out=h_out.array, n_frames=e2e_n, frame_pitch=pitch)
+        def fill(self):
+            if self.op == "color":
+                ctx.synth_bgr_device(self.d_in, self.n, self.pitch, self.W, self.H, first_frame=rank * self.n, stream=stream)
             else:
-                ctx.clahe_batch(h_in.array, W, H, args.clip, (args.tiles, args.tiles), out=h_out.array, n_frames=e2e_n,
-                                frame_pitch=pitch)
-        e2e_steps = max(2, min(args.steps, 5))
-        host_step()
-        barrier()
-        c0 = ctx.counters()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+                ctx.synth_nv12_device(self.d_in, self.n, self.pitch, self.W, self.H, seed=2026, first_frame=rank * self.n, stream=stream)
+
+        def step(self):
+            if self.op == "equalize":
+                ctx.equalize_hist_device(self.d_in, self.d_out, self.n, self.pitch, self.W, self.H, stream=stream)
+            elif self.op == "clahe":
+                ctx.clahe_device(self.d_in, self.d_out, self.n, self.pitch, self.W, self.H, args.clip, (args.tiles, args.tiles), stream=stream)
+            else:
+                ctx.color_equalize_device(self.d_in, self.d_out, self.n, self.pitch, self.W, self.H, color_mode=nv12eq.COLOR_YUV, stream=stream)
+
+        def oracle(self, frame):
+            if self.op == "equalize":
+                return O.c_nv12_equalize_hist(frame, self.W, self.H)
+            if self.op == "clahe":
+                return O.c_nv12_clahe(frame, self.W, self.H, args.clip, args.tiles, args.tiles)
+            return O.c_color_equalize(frame.reshape(self.H, self.W, 3), O.COLOR_YUV).reshape(-1)
+
+        def spot_check(self):
+            """first / middle / last frame of THIS rank's timed output against the oracle; true only if every rank agrees"""
+            ok = True
+            for k in sorted({0, self.n // 2, self.n - 1}):
+                frame = self.d_in[k * self.pitch:(k + 1) * self.pitch].cpu().numpy()
+                got = self.d_out[k * self.pitch:(k + 1) * self.pitch].cpu().numpy()
+                ok = ok and bool(np.array_equal(got, self.oracle(frame)))
+            return all_ranks_true(ok)
+
+        def measure(self, steps, warmup):
+            self.fill()
+            for _ in range(max(warmup, 3)):
+                self.step()
+            barrier()
+            launches0 = ctx.counters()["kernel_launches"]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            with ClockSampler(local) as clocks:
+                ev[0].record(stream)
+                for i in range(steps):
+                    self.step()
+                    ev[i + 1].record(stream)
+                barrier()
+            launches = ctx.counters()["kernel_launches"] - launches0
+            step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+            total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+            kernel_ms = sum(step_ms) / len(step_ms)  # one kernel launch per step: its duration is the step's
+            achieved = self.n * self.algo_bytes / (kernel_ms * 1e-3) / 1e9
+            cap = traffic_db.get(f"{self.op}_{self.size}_{self.n}")
+            traffic, traffic_note = None, "no ncu capture for this workload"
+            if isinstance(cap, dict):
+                if cap.get("kernel_src_sha") == src_sha:
+                    traffic, traffic_note = cap.get("dram_bytes"), f"ncu --set full capture of these kernel sources ({src_sha})"
+                else:
+                    traffic_note = f"stale: capture was taken on kernel sources {cap.get('kernel_src_sha')}, this build is {src_sha}"
+            return {
+                "value": world * self.n * steps / (total_ms * 1e-3), "unit": "frames/s", "steps": steps, "ms_per_step": total_ms / steps,
+                "workload": workload_name(self.op, args.clip, args.tiles, self.n, self.W, self.H),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "kernel": self.kernel,
+                             "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": self.n * self.algo_bytes},
+                "gpu_launches": launches, "clocks": clocks.summary(), "parity_spot_check": self.spot_check(),
+                "step_ms_min": min(step_ms), "step_ms_max": max(step_ms)}
+
+        def sustain(self, seconds):
+            """back-to-back launches for `seconds`: the board reaches its 1 kW cap after ~2 s and the SM clock drops"""
+            self.fill()
+            self.step()
+            barrier()
+            ev, t0 = [torch.cuda.Event(enable_timing=True)], time.perf_counter()
+            with ClockSampler(local, period=0.02) as clocks:
+                ev[0].record(stream)
+                while time.perf_counter() - t0 < seconds:
+                    for _ in range(8):
+                        self.step()
+                        e = torch.cuda.Event(enable_timing=True)
+                        e.record(stream)
+                        ev.append(e)
+                    ev[-1].synchronize()   # keep the queue short so that the wall clock bounds the leg
+                barrier()
+            ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(ev) - 1)]
+            tail, acc = [], 0.0
+            for x in reversed(ms):        # the launches of the last second
+                tail.append(x)
+                acc += x
+                if acc >= 1000.0:
+                    break
+            tail_ms = max_over_ranks(sum(tail) / len(tail))
+            all_ms = max_over_ranks(sum(ms) / len(ms))
+            fps = world * self.n / (tail_ms * 1e-3)
+            return {"value_sustained": fps, "unit": "frames/s", "seconds": sum(ms) / 1e3, "launches": len(ms),
+                    "ms_per_launch_last_second": tail_ms, "ms_per_launch_all": all_ms, "ms_per_launch_first": ms[0],
+                    "frac_sustained": fps / world * self.algo_bytes / 1e9 / peak, "clocks": clocks.summary()}
+
+        def e2e(self, steps):
+            """the same batch through the host C-ABI batch call with pinned HOST buffers, copies inside the timed region"""
+            e2e_n = self.n
+            try:
+                h_in, h_out = nv12eq.PinnedBuffer(e2e_n * self.pitch), nv12eq.PinnedBuffer(e2e_n * self.pitch)
+            except nv12eq.Nv12eqError:
+                e2e_n = max(8, self.n // 8)
+                h_in, h_out = nv12eq.PinnedBuffer(e2e_n * self.pitch), nv12eq.PinnedBuffer(e2e_n * self.pitch)
+            self.fill()
+            self.step()
+            torch.cuda.synchronize()
+            torch.from_numpy(h_in.array).copy_(self.d_in[:e2e_n * self.pitch])   # outside the timed region
+            torch.cuda.synchronize()
+
+            def host_step():
+                if self.op == "equalize":
+                    ctx.equalize_hist_batch(h_in.array, self.W, self.H, out=h_out.array, n_frames=e2e_n, frame_pitch=self.pitch)
+                else:
+                    ctx.clahe_batch(h_in.array, self.W, self.H, args.clip, (args.tiles, args.tiles), out=h_out.array, n_frames=e2e_n,
+                                    frame_pitch=self.pitch)
             host_step()
-        barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        c1 = ctx.counters()
-        ok = True
-        if rank == 0:
-            ok = bool(np.array_equal(h_out.array[(e2e_n - 1) * pitch:e2e_n * pitch],
-                                     d_out[(e2e_n - 1) * pitch:e2e_n * pitch].cpu().numpy()))
-        # bytes that actually crossed PCIe, from the library's own counters: in passthrough mode only the luma planes
-        # move (W*H of the 1.5*W*H bytes of a frame, each way); the chroma is copied host-to-host by the library's
-        # host threads, as the reference does with memcpy (nextimprovement.cpp:160)
-        e2e = {"value": world * e2e_n * e2e_steps / e2e_s, "unit": "frames/s",
-               "h2d_bytes_per_step": (c1["bytes_in"] - c0["bytes_in"]) // e2e_steps,
-               "d2h_bytes_per_step": (c1["bytes_out"] - c0["bytes_out"]) // e2e_steps,
-               "host_frame_bytes_per_step": e2e_n * pitch, "frames_per_step": e2e_n, "steps": e2e_steps,
-               "api": "nv12eq_equalize_hist_batch" if args.op == "equalize" else "nv12eq_clahe_batch",
-               "host_memory": "pinned (nv12eq_host_alloc)", "chroma": "host memcpy inside the call (never crosses PCIe)",
-               "matches_device_leg": ok}
-        h_in.free(); h_out.free()
+            barrier()
+            c0 = ctx.counters()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                host_step()
+            barrier()
+            e2e_s = max_over_ranks(time.perf_counter() - t0)
+            c1 = ctx.counters()
+            ok = True
+            for k in sorted({0, e2e_n // 2, e2e_n - 1}):
+                ok = ok and bool(np.array_equal(h_out.array[k * self.pitch:(k + 1) * self.pitch],
+                                                self.d_out[k * self.pitch:(k + 1) * self.pitch].cpu().numpy()))
+            ok = all_ranks_true(ok)
+            # bytes that actually crossed PCIe, from the library's own counters: in passthrough mode only the luma planes
+            # move (W*H of the 1.5*W*H bytes of a frame, each way); the chroma is copied host-to-host by the library's
+            # host threads, as the reference does with memcpy (nextimprovement.cpp:160)
+            rec = {"value": world * e2e_n * steps / e2e_s, "unit": "frames/s",
+                   "h2d_bytes_per_step": (c1["bytes_in"] - c0["bytes_in"]) // steps,
+                   "d2h_bytes_per_step": (c1["bytes_out"] - c0["bytes_out"]) // steps,
+                   "host_frame_bytes_per_step": e2e_n * self.pitch, "frames_per_step": e2e_n, "steps": steps,
+                   "api": "nv12eq_equalize_hist_batch" if self.op == "equalize" else "nv12eq_clahe_batch",
+                   "host_memory": "pinned (nv12eq_host_alloc)", "chroma": "host memcpy inside the call (never crosses PCIe)",
+                   "lanes": ctx.slots, "matches_device_leg": ok}
+            # what the box's PCIe / host memory gives when the same luma bytes are only copied (both directions at once,
+            # every rank at the same time): the ceiling of this leg
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+            hin_t, hout_t = torch.from_numpy(h_in.array), torch.from_numpy(h_out.array)
+            nbytes = min(e2e_n * self.pitch, 1 << 30)
+
+            def copy_both():
+                with torch.cuda.stream(s1):
+                    self.d_in[:nbytes].copy_(hin_t[:nbytes], non_blocking=True)
+                with torch.cuda.stream(s2):
+                    hout_t[:nbytes].copy_(self.d_out[:nbytes], non_blocking=True)
+            copy_both()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                copy_both()
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            gbs = 4 * nbytes / dt / 1e9
+            ceiling = world * gbs * 1e9 / (self.W * self.H)
+            rec.update({"copy_ceiling_gbs_per_direction_per_gpu": gbs, "copy_ceiling_frames_per_sec": ceiling,
+                        "frac_of_copy_ceiling": rec["value"] / ceiling})
+            h_in.free(); h_out.free()
+            return rec
+
+    workloads = {key: Workload(key, op, size, n) for key, op, size, n in specs}
+    head = workloads["headline"]
+    results = {}
+    for key, wl in workloads.items():
+        steps = args.steps if key == "headline" else max(args.steps, 20)
+        results[key] = wl.measure(steps, args.warmup)
+        time.sleep(0.3)   # let the board's power estimate settle between cells: every cell is a short burst
+    sustained = {}
+    if args.sustain_seconds > 0:
+        for key, wl in workloads.items():
+            if wl.size == "4k" and wl.op in ("equalize", "clahe"):
+                time.sleep(1.0)
+                sustained["equalize_4k" if key == "headline" and wl.op == "equalize" else key] = wl.sustain(args.sustain_seconds)
+    e2e, e2e_extra = None, {}
+    if not args.no_e2e:
+        e2e_steps = max(2, min(args.steps, 5))
+        if head.op != "color":
+            e2e = head.e2e(e2e_steps)
+        if "clahe_4k" in workloads:
+            e2e_extra["clahe_4k"] = workloads["clahe_4k"].e2e(e2e_steps)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks, peak_src = None, "fallback (B200_PROFILING.md): 6650 GB/s"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        peak = 6650.0
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            t = json.load(f)
-        traffic = t.get(f"{args.op}_{args.size}_{n}", None)
-    except Exception:
-        pass
-
     cpu = None
     if world == 1 and not args.no_cpu:
-        nf = calibrate_cpu_frames(args, W, H, args.cpu_seconds, 3)
-        # about --cpu-seconds (default 12) of CPU work in total: the frame count is capped by host memory, so the number of
-        # passes over the sample makes up the rest
-        passes = int(max(2, min(40, round(args.cpu_seconds / (nf * calibrate_cpu_frames.per_frame_s)))))
-        r = cpu_leg(args, W, H, nf, passes, 1)
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        W, H = head.W, head.H
+        # bounded sample: about --cpu-seconds (default 12) core-seconds of CPU work; --impl reference runs the full batch
+        nf = min(head.n, 64)
+        one = cpu_one_thread(args, head.op, W, H, cpu_frames(head.op, W, H, 1)[0], seconds=0.5) or 50.0
+        passes = int(max(2, min(40, round(args.cpu_seconds * one / nf))))
+        r = cpu_leg(args, head.op, W, H, nf, passes, 1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "one_thread_value", "cpu_model", "host_cores")}
 
+    h = results.pop("headline")
     line = {
-        "metric": "nv12_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(args, W, H), "op": args.op, "width": W, "height": H, "frames_per_gpu": n,
-                   "uv": "passthrough", "l2": f"inputs {n * pitch / 1e9:.2f} GB per GPU > 126 MB L2, no flush needed",
-                   "parallelism": f"frame-sharded x{world}, no collective", "tuning": {"chunks": args.chunks, "lag": args.lag,
-                                                                                      "ctas": args.ctas, "schedule": args.schedule}},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "equalize_kernel" if args.op == "equalize" else "clahe_kernel",
-                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": n * bytes_per_frame_algo},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
-        "parity_spot_check": parity, "step_ms_min": min(step_ms), "step_ms_max": max(step_ms),
+        "metric": "nv12_frames_per_sec", "value": h["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_of(args, head.W, head.H),
+        "roofline": h["roofline"], "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": h["gpu_launches"], "clocks": h["clocks"],
+        "parity_spot_check": h["parity_spot_check"], "step_ms_min": h["step_ms_min"], "step_ms_max": h["step_ms_max"],
+        "kernel_src_sha": src_sha,
     }
+    if results:
+        for key, rec in results.items():
+            if key in e2e_extra:
+                rec["e2e"] = e2e_extra[key]
+        line["workloads"] = results
+    if sustained:
+        line["sustained"] = sustained
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

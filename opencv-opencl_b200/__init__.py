@@ -557,6 +557,12 @@ class Stream:
 _default_ctx: Optional[Context] = None
 
 
+def default_slots() -> int:
+    """Host lanes a context gets by default for batch calls: three, so that an upload, a kernel and a download are always
+    queued on different lanes (two lanes leave the copy engines idle while the host re-arms a lane)."""
+    return 3
+
+
 def default_context() -> Context:
     global _default_ctx
     if _default_ctx is None:

@@ -78,19 +78,25 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 //   first read of the Y plane  -> evict_last  : it is read again by the apply / interpolation pass a few frames later
 //   second read, chroma, output-> evict_first : streaming data must not push the Y planes out of the 126 MB L2
 // 256-bit accesses (one 32-byte sector-pair per thread) halve the number of load/store instructions.
+// The loads are coherent ld.global (no .nc): in-place calls (in == out, supported and tested) store to the very addresses
+// the same kernel loads from, and PTX only allows .nc for data that is read-only for the whole kernel.  The L1 bypass and
+// the L2 eviction priorities are what matter for speed, not the non-coherent path (A/B: -DNV12EQ_NC='".nc"').
+#ifndef NV12EQ_NC
+#define NV12EQ_NC ""
+#endif
 struct V8 {
     uint32_t r[8];
 };
 __device__ __forceinline__ V8 ldg256_keep(const void* p) {
     V8 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global" NV12EQ_NC ".L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
                  : "l"(p));
     return v;
 }
 __device__ __forceinline__ V8 ldg256_stream(const void* p) {
     V8 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global" NV12EQ_NC ".L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
                  : "l"(p));
     return v;
@@ -115,14 +121,14 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 }
 __device__ __forceinline__ int4 ldg128_hint(const void* p, uint64_t pol) {
     int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+    asm volatile("ld.global" NV12EQ_NC ".L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p), "l"(pol));
     return r;
 }
 __device__ __forceinline__ uint2 ldg64_hint(const void* p, uint64_t pol) {
     uint2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+    asm volatile("ld.global" NV12EQ_NC ".L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
     return r;
 }
 __device__ __forceinline__ void stg64_hint(void* p, uint2 v, uint64_t pol) {

@@ -273,6 +273,15 @@ int ws_reserve_frames(nv12eq_ctx* ctx, Workspace& w, int frames) {
     w.frames_cap = cap;
     return NV12EQ_OK;
 }
+// The kernels' sticky status word: non-zero when a dependency wait timed out (a logic error; cannot happen by construction).
+// The CTAs that gave up leave histograms and counters non-zero, so the workspace is put back to its zero state before
+// the next launch can trip over it.  Call with the stream idle.
+void ws_reset(Workspace& w, cudaStream_t st) {
+    if (w.misc.p) cudaMemsetAsync(w.misc.p, 0, w.misc.cap, st);
+    if (w.hist.p) cudaMemsetAsync(w.hist.p, 0, w.hist.cap, st);
+    if (w.counters.p) cudaMemsetAsync(w.counters.p, 0, w.counters.cap, st);
+    cudaStreamSynchronize(st);
+}
 uint32_t* ws_counter(Workspace& w, int which) { return reinterpret_cast<uint32_t*>(w.counters.p) + (size_t)which * w.frames_cap; }
 uint32_t* ws_ticket(Workspace& w) { return reinterpret_cast<uint32_t*>(w.misc.p); }
 uint32_t* ws_status(Workspace& w) { return reinterpret_cast<uint32_t*>(w.misc.p) + 1; }
@@ -362,6 +371,7 @@ int launch_equalize(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t
         p.phases = phases;
         const bool both = (phases & PH_HIST) && (phases & PH_APPLY);
         long long items = (long long)(n + (both ? p.lag : 0)) * 2 * C;
+        if (items >= (1ll << 32)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "too many work items (%lld): split the batch", items);
         int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * per_sm, items));
         if (per_sm <= 1) equalize_kernel<1><<<grid, kThreads, smem, st>>>(p);
         else if (per_sm == 2) equalize_kernel<2><<<grid, kThreads, smem, st>>>(p);
@@ -569,6 +579,7 @@ int launch_color_fused(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint
     p.ticket = ws_ticket(ws);
     p.status = ws_status(ws);
     const long long items = (long long)(n + p.lag) * 2 * C;
+    if (items >= (1ll << 32)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "too many work items (%lld): split the batch", items);
     const int grid = (int)std::max<long long>(1, std::min<long long>(ctas, items));
     color_equalize_kernel<2><<<grid, kThreads, kColorEqSmemBytes, st>>>(p);
     ctx->ctr.kernel_launches++;
@@ -685,27 +696,36 @@ int lane_submit_nv12(nv12eq_ctx* ctx, Lane& L, const Job& j) {
     uint8_t* d_in = reinterpret_cast<uint8_t*>(L.d_in.p);
     uint8_t* d_out = in_place ? d_in : reinterpret_cast<uint8_t*>(L.d_out.p);
 
+    // everything that can fail without touching the device happens before the first copy is queued: a caller that sees an
+    // error may free or reuse its buffers at once
+    if (j.op == Op::Clahe && (j.tx < 1 || j.ty < 1 || (long long)j.tx * j.ty > (1 << 20)))
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", j.tx, j.ty);
+    const bool in_pinned = is_pinned(j.in), out_pinned = is_pinned(j.out);
+    if (!in_pinned && (rc = host_reserve(ctx, L.h_in, span))) return rc;
+    if (!out_pinned && (rc = host_reserve(ctx, L.h_out, span))) return rc;
+    if ((rc = ws_reserve_frames(ctx, L.ws, j.n))) return rc;
     const uint8_t* src = j.in;
-    if (!is_pinned(j.in)) {  // pageable caller memory: stage the luma through pinned memory so the DMA is asynchronous
-        if ((rc = host_reserve(ctx, L.h_in, span))) return rc;
+    if (!in_pinned) {  // pageable caller memory: stage the luma through pinned memory so the DMA is asynchronous
         copy_luma_host(reinterpret_cast<uint8_t*>(L.h_in.p), j.in, j.n, j.pitch, j.w, j.h, j.stride);
         src = reinterpret_cast<const uint8_t*>(L.h_in.p);
     }
-    if ((rc = copy_luma_async(ctx, d_in, src, j, cudaMemcpyHostToDevice, L.stream))) return rc;
+    // from here on copies from / to the caller's buffers may be in flight: a failure drains the lane before it is reported
+    auto drained = [&](int status) { cudaStreamSynchronize(L.stream); return status; };
+    if ((rc = copy_luma_async(ctx, d_in, src, j, cudaMemcpyHostToDevice, L.stream))) return drained(rc);
     ctx->ctr.bytes_in += luma_payload(j);
     if (j.op == Op::Equalize) rc = launch_equalize(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, UV_SKIP, L.stream);
     else rc = launch_clahe(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.clip, j.tx, j.ty, UV_SKIP, L.stream);
-    if (rc) return rc;
+    if (rc) return drained(rc);
     uint8_t* dst = j.out;
     L.user_out = nullptr;
-    if (!is_pinned(j.out)) {
-        if ((rc = host_reserve(ctx, L.h_out, span))) return rc;
+    if (!out_pinned) {
         dst = reinterpret_cast<uint8_t*>(L.h_out.p);
         L.user_out = j.out;
     }
-    if ((rc = copy_luma_async(ctx, dst, d_out, j, cudaMemcpyDeviceToHost, L.stream))) return rc;
-    CK(ctx, cudaMemcpyAsync(L.h_status, ws_status(L.ws), sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream));
-    CK(ctx, cudaEventRecord(L.done, L.stream));
+    if ((rc = copy_luma_async(ctx, dst, d_out, j, cudaMemcpyDeviceToHost, L.stream))) return drained(rc);
+    if (cudaMemcpyAsync(L.h_status, ws_status(L.ws), sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream) != cudaSuccess ||
+        cudaEventRecord(L.done, L.stream) != cudaSuccess)
+        return drained(fail(ctx, NV12EQ_ERR_CUDA, "queuing the completion of a lane failed: %s", cudaGetErrorString(cudaGetLastError())));
     ctx->ctr.bytes_out += luma_payload(j);
     host_chroma(ctx, L, j);  // overlaps with the GPU work queued above
     L.luma_only = true;
@@ -729,45 +749,59 @@ int lane_submit(nv12eq_ctx* ctx, Lane& L, const Job& j) {
     uint8_t* d_in = reinterpret_cast<uint8_t*>(L.d_in.p);
     uint8_t* d_out = in_place ? d_in : reinterpret_cast<uint8_t*>(L.d_out.p);
 
+    if (j.op == Op::ColorClahe && (j.tx < 1 || j.ty < 1 || (long long)j.tx * j.ty > (1 << 20)))
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", j.tx, j.ty);
+    const bool in_pinned = is_pinned(j.in), out_pinned = is_pinned(j.out);
+    if (!in_pinned && (rc = host_reserve(ctx, L.h_in, span))) return rc;
+    if (!out_pinned && (rc = host_reserve(ctx, L.h_out, span))) return rc;
+    if ((rc = ws_reserve_frames(ctx, L.ws, j.n))) return rc;
     const uint8_t* src = j.in;
-    if (!is_pinned(j.in)) {  // pageable caller memory: stage through pinned memory so the DMA is asynchronous
-        if ((rc = host_reserve(ctx, L.h_in, span))) return rc;
+    if (!in_pinned) {  // pageable caller memory: stage through pinned memory so the DMA is asynchronous
         memcpy(L.h_in.p, j.in, span);
         src = reinterpret_cast<const uint8_t*>(L.h_in.p);
     }
-    CK(ctx, cudaMemcpyAsync(d_in, src, span, cudaMemcpyHostToDevice, L.stream));
+    auto drained = [&](int status) { cudaStreamSynchronize(L.stream); return status; };
+    auto cuda_fail = [&](const char* what) { return drained(fail(ctx, NV12EQ_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(cudaGetLastError()))); };
+    if (cudaMemcpyAsync(d_in, src, span, cudaMemcpyHostToDevice, L.stream) != cudaSuccess) return cuda_fail("upload");
     ctx->ctr.bytes_in += span;
     // With strided rows the padding bytes of the caller's output must survive: the device image starts from them.
     const bool preserve_bgr = !in_place && (j.stride != 3 * j.w);
     if (preserve_bgr) {
         const uint8_t* osrc = j.out;
-        if (!is_pinned(j.out)) {
-            if ((rc = host_reserve(ctx, L.h_out, span))) return rc;
+        if (!out_pinned) {
             memcpy(L.h_out.p, j.out, span);
             osrc = reinterpret_cast<const uint8_t*>(L.h_out.p);
         }
-        CK(ctx, cudaMemcpyAsync(d_out, osrc, span, cudaMemcpyHostToDevice, L.stream));
+        if (cudaMemcpyAsync(d_out, osrc, span, cudaMemcpyHostToDevice, L.stream) != cudaSuccess) return cuda_fail("upload of the output padding");
         ctx->ctr.bytes_in += span;
     }
     rc = launch_color(ctx, L.ws, d_in, d_out, j.n, j.pitch, j.w, j.h, j.stride, j.color_mode, j.op == Op::ColorClahe, j.clip, j.tx,
                       j.ty, L.stream);
-    if (rc) return rc;
+    if (rc) return drained(rc);
     uint8_t* dst = j.out;
     L.user_out = nullptr;
-    if (!is_pinned(j.out)) {
-        if ((rc = host_reserve(ctx, L.h_out, span))) return rc;
+    if (!out_pinned) {
         dst = reinterpret_cast<uint8_t*>(L.h_out.p);
         L.user_out = j.out;
     }
-    CK(ctx, cudaMemcpyAsync(dst, d_out, span, cudaMemcpyDeviceToHost, L.stream));
-    CK(ctx, cudaMemcpyAsync(L.h_status, ws_status(L.ws), sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream));
-    CK(ctx, cudaEventRecord(L.done, L.stream));
+    if (cudaMemcpyAsync(dst, d_out, span, cudaMemcpyDeviceToHost, L.stream) != cudaSuccess ||
+        cudaMemcpyAsync(L.h_status, ws_status(L.ws), sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream) != cudaSuccess ||
+        cudaEventRecord(L.done, L.stream) != cudaSuccess)
+        return cuda_fail("download");
     ctx->ctr.bytes_out += span;
     L.luma_only = false;
     L.out_bytes = span;
     L.frames = j.n;
     L.busy = true;
     return NV12EQ_OK;
+}
+
+// After the lane's stream has been synchronised and its status word copied to L.h_status.
+int lane_status(nv12eq_ctx* ctx, Lane& L) {
+    if (!L.h_status || *L.h_status == 0) return NV12EQ_OK;
+    *L.h_status = 0;
+    ws_reset(L.ws, L.stream);
+    return fail(ctx, NV12EQ_ERR_CUDA, "kernel dependency wait timed out; the workspace has been reset");
 }
 
 int lane_wait(nv12eq_ctx* ctx, Lane& L) {
@@ -777,10 +811,8 @@ int lane_wait(nv12eq_ctx* ctx, Lane& L) {
     CK(ctx, cudaEventSynchronize(L.done));
     if (*L.h_status != 0) {
         // a kernel gave up waiting (should be impossible); put the workspace back to a known state
-        cudaMemsetAsync(L.ws.misc.p, 0, L.ws.misc.cap, L.stream);
-        if (L.ws.hist.p) cudaMemsetAsync(L.ws.hist.p, 0, L.ws.hist.cap, L.stream);
-        if (L.ws.counters.p) cudaMemsetAsync(L.ws.counters.p, 0, L.ws.counters.cap, L.stream);
-        cudaStreamSynchronize(L.stream);
+        *L.h_status = 0;
+        ws_reset(L.ws, L.stream);
         return fail(ctx, NV12EQ_ERR_CUDA, "kernel dependency wait timed out");
     }
     if (L.user_out) {
@@ -1078,6 +1110,20 @@ int nv12eq_sync(nv12eq_ctx* ctx) {
     if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(ctx->device);
     CK(ctx, cudaStreamSynchronize(ctx->own_stream));
+    // the *_device forms never synchronise, so this is where their kernels' status word is read: wait for the stream of the
+    // last device call, fetch the word, and on a (never expected) dependency time-out put the workspace back to zero
+    if (ctx->dev_ws_used && ctx->dev_ws.misc.p) {
+        if (ctx->dev_ws_stream != ctx->own_stream && cudaStreamSynchronize(ctx->dev_ws_stream) != cudaSuccess) {
+            cudaGetLastError();   // the caller destroyed that stream: its work is complete or will never run
+            CK(ctx, cudaDeviceSynchronize());
+        }
+        uint32_t st = 0;
+        CK(ctx, cudaMemcpy(&st, ws_status(ctx->dev_ws), sizeof st, cudaMemcpyDeviceToHost));
+        if (st != 0) {
+            ws_reset(ctx->dev_ws, ctx->own_stream);
+            return fail(ctx, NV12EQ_ERR_CUDA, "kernel dependency wait timed out in a *_device call; the workspace has been reset");
+        }
+    }
     return NV12EQ_OK;
 }
 
@@ -1218,7 +1264,9 @@ static int meta_frame(nv12eq_ctx* ctx, Op op, const uint8_t* in, size_t in_size,
                 else memset(dst + (size_t)r * O.stride[1], 128, (size_t)w);
             }
     }
+    CK(ctx, cudaMemcpyAsync(L.h_status, ws_status(L.ws), sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream));
     CK(ctx, cudaStreamSynchronize(L.stream));
+    if ((rc = lane_status(ctx, L))) return rc;
     ctx->ctr.bytes_in += plane; ctx->ctr.bytes_out += plane; ctx->ctr.frames++;
     ctx->ctr.busy_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     return NV12EQ_OK;
@@ -1473,6 +1521,7 @@ int stream_launch(nv12eq_stream* s, Lane& L) {
                              : launch_equalize(ctx, L.ws, d_in, d_out, 1, j.pitch, j.w, j.h, j.stride, UV_SKIP, L.stream);
     if (rc) return rc;
     if ((rc = copy_luma_async(ctx, j.out, d_out, j, cudaMemcpyDeviceToHost, L.stream))) return rc;
+    CK(ctx, cudaMemcpyAsync(L.h_status, ws_status(L.ws), sizeof(uint32_t), cudaMemcpyDeviceToHost, L.stream));
     CK(ctx, cudaEventRecord(L.done, L.stream));
     return NV12EQ_OK;
 }
@@ -1505,6 +1554,8 @@ int nv12eq_stream_open(nv12eq_ctx* ctx, const nv12eq_stream_config* cfg, nv12eq_
     for (auto& L : s->lanes) {
         bool ok = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&L.h_status), sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
+        if (ok) *L.h_status = 0;
         if (ok) rc = dev_reserve(ctx, L.d_in, s->frame_bytes, false);
         if (ok && !rc) rc = dev_reserve(ctx, L.d_out, s->frame_bytes, true);
         if (ok && !rc) rc = host_reserve(ctx, L.h_in, s->frame_bytes);
@@ -1609,6 +1660,19 @@ int nv12eq_stream_pop(nv12eq_stream* s, uint8_t* out, size_t out_size, uint64_t*
         lk.unlock();
         return nv12eq_stream_pop(s, out, out_size, out_seq, block);
     }
+    if (*L.h_status != 0) {
+        // a kernel of this lane gave up on a dependency wait (never expected): the frame is not valid.  Reset the lane's
+        // workspace and deliver the failure in the frame's place -- the consumer drops it like any failed frame.
+        *L.h_status = 0;
+        ws_reset(L.ws, L.stream);
+        s->head = (s->head + 1) % depth;
+        s->count--;
+        s->st.in_flight = s->count;
+        if (out_seq) *out_seq = q;
+        lk.unlock();
+        s->cv.notify_all();
+        return stream_fail(s, NV12EQ_ERR_CUDA, "kernel dependency wait timed out; the frame is dropped and the lane has been reset");
+    }
     // copy out under the lock: a DROP_OLDEST producer must not recycle the lane while it is being read
     {
         const int H = s->cfg.height;
@@ -1641,6 +1705,7 @@ void nv12eq_stream_close(nv12eq_stream* s) {
         if (L.stream) cudaStreamSynchronize(L.stream);
         dev_release(L.d_in); dev_release(L.d_out); host_release(L.h_in); host_release(L.h_out);
         ws_release(L.ws);
+        if (L.h_status) cudaFreeHost(L.h_status);
         if (L.done) cudaEventDestroy(L.done);
         if (L.stream) cudaStreamDestroy(L.stream);
     }

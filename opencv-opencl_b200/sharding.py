@@ -272,20 +272,20 @@ class SpatialSplitEqualizer:
         self.band = row_bands(height, world, 2)[rank]
 
     def run(self, d_band_in, d_band_out, stream=None):
+        """`stream`: a torch.cuda.Stream, or None for torch's current stream.  Everything -- the zero fill of the histogram,
+        the histogram kernel, the all-reduce and the apply kernel -- is queued on that ONE stream (made torch's current
+        stream for the duration), so the steps are ordered by the stream and nothing has to be drained in between."""
         import torch
+        if stream is not None and not isinstance(stream, torch.cuda.Stream):
+            raise TypeError("SpatialSplitEqualizer.run: stream must be a torch.cuda.Stream or None (torch's current stream)")
+        st = stream if stream is not None else torch.cuda.current_stream(d_band_in.device)
         first, rows = self.band
-        hist = torch.zeros(256, dtype=torch.int32, device=d_band_in.device)
-        if rows > 0:
-            self.ctx.hist_device(d_band_in, 1, self.width * rows, self.width, rows, hist, stream=stream)
-        # torch's NCCL all-reduce is ordered after the work already queued on the current torch stream; only the context's
-        # own stream (stream=None) is invisible to torch and has to be drained first
-        if stream is None:
-            self.ctx.sync()
-        allreduce_histograms(hist, self.group)
-        if stream is None:
-            import torch
-            torch.cuda.current_stream().synchronize()   # the all-reduce ran on torch's stream; the apply runs on ours
-        if rows > 0:
-            self.ctx.equalize_apply_device(d_band_in, d_band_out, 1, self.width * rows, self.width, rows, hist,
-                                           self.width * self.height, stream=stream)
+        with torch.cuda.stream(st):
+            hist = torch.zeros(256, dtype=torch.int32, device=d_band_in.device)
+            if rows > 0:
+                self.ctx.hist_device(d_band_in, 1, self.width * rows, self.width, rows, hist, stream=st)
+            allreduce_histograms(hist, self.group)   # NCCL work is ordered on torch's current stream = st
+            if rows > 0:
+                self.ctx.equalize_apply_device(d_band_in, d_band_out, 1, self.width * rows, self.width, rows, hist,
+                                               self.width * self.height, stream=st)
         return hist

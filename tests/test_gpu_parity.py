@@ -272,7 +272,7 @@ def test_full_size_config2_equalize_4k_batch(nv, ctx, oracle, golden, torch):
 def test_full_size_clahe_1080p_and_4k(nv, ctx, oracle, golden, torch):
     """BASELINE configs 3/4: CLAHE clip 2.0, 8x8 on 1080p and 4K streams (device resident batches)."""
     st = torch.cuda.current_stream()
-    for (W, H, n, probes) in [(1920, 1080, 64, (2, 31, 63)), (3840, 2160, 32, (2, 31))]:
+    for (W, H, n, probes) in [(1920, 1080, 256, (2, 127, 255)), (3840, 2160, 256, (2, 31, 128, 255))]:  # the bench's batch sizes
         pitch = nv.nv12_frame_bytes(W, H)
         d_in = torch.empty(n * pitch, dtype=torch.uint8, device="cuda")
         d_out = torch.zeros_like(d_in)

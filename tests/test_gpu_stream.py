@@ -1,5 +1,6 @@
 """GPU tests of the ordered, back-pressured frame stream (nv12eq_stream_*) and of the
 round-robin dispatcher on top of it.  Results are compared bit-exactly with the oracle through the C-ABI."""
+import os
 import threading
 
 import numpy as np
@@ -154,6 +155,55 @@ def test_spatial_split_equalizer_single_rank(nv, ctx, oracle):
     torch.cuda.synchronize()
     assert np.array_equal(hist.cpu().numpy(), oracle.c_hist256(y.reshape(H, W)))
     assert np.array_equal(d_out.cpu().numpy().reshape(H, W), oracle.c_equalize_hist(y.reshape(H, W)))
+
+
+def _spatial_split_worker(rank, world, port, q):
+    """one rank of the 2-GPU spatial split: own band of one 4K luma plane, NCCL all-reduce of the 256-bin histogram"""
+    import torch
+    import torch.distributed as dist
+    import opencv_opencl_b200 as nv
+    from oracle import oracle as O
+    try:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
+        W, H = 3840, 2160
+        y = O.c_synth_nv12(W, H, 2026, 3)[:W * H].reshape(H, W)
+        want = O.c_equalize_hist(y)
+        ok = True
+        with nv.Context(rank, W, H, 1) as ctx:
+            eq = nv.sharding.SpatialSplitEqualizer(ctx, W, H, rank, world)
+            first, rows = eq.band
+            d_in = torch.from_numpy(np.ascontiguousarray(y[first:first + rows]).reshape(-1)).cuda()
+            for stream in (None, torch.cuda.Stream()):       # torch's current stream, and a side stream (ADVICE r1)
+                d_out = torch.zeros_like(d_in)
+                for _ in range(3):                           # repeated: a racing zero-fill would corrupt a later run
+                    hist = eq.run(d_in, d_out, stream=stream)
+                torch.cuda.synchronize()
+                ok = ok and np.array_equal(hist.cpu().numpy(), O.c_hist256(y))
+                ok = ok and np.array_equal(d_out.cpu().numpy().reshape(rows, W), want[first:first + rows])
+        dist.destroy_process_group()
+        q.put((rank, bool(ok), ""))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, False, repr(e)))
+
+
+def test_spatial_split_equalizer_two_gpus(nv):
+    """SURVEY 8e optional mode with a real exchange: two ranks, two GPUs, one NCCL all-reduce per frame."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctxmp.Process(target=_spatial_split_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok, _ in res), res
 
 
 def test_cpp_example_runs_both_modes(nv):
