@@ -29,44 +29,66 @@
 #pragma once
 #include "common.cuh"
 
-// Dynamic shared memory of clahe_kernel, declared at global scope so that its PTX name is unmangled: the kernel takes
-// its address with `mov.u32 r, nv12eq_smem_rows`, a plain shared-window offset (cvta would add the CTA's cluster-window
-// bits), which keeps ring and table addresses simple register + immediate forms.
+// Dynamic shared memory of clahe_kernel.  The kernel owns ALL of its shared memory through this one array (no static
+// __shared__ variables), so the array starts at a fixed offset of the CTA's shared window: kSmemBase, the 1 KB the system
+// reserves at the bottom of the window on sm_90+/sm_100.  Knowing the base at compile time lets every table access be
+// `[register + immediate]` with the register formed by ONE PRMT (see row_off): the kernel verifies the assumption when it
+// starts and refuses to run otherwise (status word 2 -> NV12EQ_ERR_CUDA on the host).
 extern __shared__ __align__(256) uint32_t nv12eq_smem_rows[];
 
 namespace nv12eq {
 
 constexpr int kMaxCells = 4096;  // per axis (tiles + 1); plenty
 constexpr int kMaxCellRows = 512;               // rows per interpolation cell (host cuts longer runs)
+constexpr int kParamCells = 20;                 // cells per axis that fit the kernel parameters (an 8x8 .. 16x16 grid has 9 .. 17)
 // CTA shape of clahe_kernel (compile-time; the Makefile's EXTRA can override for experiments):
-//   256 threads x 4 (or 3) CTAs/SM with 128-byte table rows (32 KB table) -- the default: several independent items per SM
-//       fill the bubbles of the per-item phases (table build, LUT warp, barriers); measured 8.1 us vs 9.1 us per 4K frame
-//       and 2.6 us vs 3.6 us per 1080p frame against
-//   512 threads x 2 CTAs/SM with 256-byte table rows (one-PRMT addressing, 64 KB table).
-//   The host launches the <kClaheCtas - 1> instantiation (more registers per thread) for tiles of 256 K pixels and more.
-#ifndef NV12EQ_CLAHE_THREADS
-#define NV12EQ_CLAHE_THREADS 256
-#endif
-#ifndef NV12EQ_CLAHE_ROWSHIFT
-#define NV12EQ_CLAHE_ROWSHIFT 7
-#endif
+//   A CTA is kGroups = 2 independent WORK GROUPS of kCT = 256 threads ("virtual CTAs"): each group draws its own tickets and
+//   synchronises on its own named barrier, exactly as a 256-thread CTA would.  Two CTAs per SM = four groups per SM = 32
+//   warps at 64 registers per thread: several independent items per SM fill the bubbles of the per-item phases (table build,
+//   LUT build, dependency waits, barriers) -- the reason round 1 preferred four small CTAs to two large ones.
+//   What the two groups SHARE is one set of 256 table rows of 256 bytes:
+//     bytes [g * 128, g * 128 + 128) of row v: group g's hist[v][32 lanes] u32 (tile item) or table[v][16 replicas] of 8-byte
+//     entries (cell item).
+//   A 256-byte pitch turns a pixel byte into its row offset with ONE PRMT (byte 1 = pixel value, byte 0 = the lane's offset
+//   inside the row, which carries the group's half); with 128-byte rows every access needs an extra multiply-add (round 1:
+//   24 thread-instructions per pixel, issue-bound).  Four real 256-thread CTAs per SM could not afford 64 KB of rows each.
 #ifndef NV12EQ_CLAHE_CTAS
-#define NV12EQ_CLAHE_CTAS 4
+#define NV12EQ_CLAHE_CTAS 2
 #endif
-constexpr int kCT = NV12EQ_CLAHE_THREADS;       // threads per CTA
+#ifndef NV12EQ_CLAHE_SMEM_BASE
+#define NV12EQ_CLAHE_SMEM_BASE 1024
+#endif
+#ifndef NV12EQ_CLAHE_DEPTH
+#define NV12EQ_CLAHE_DEPTH 4
+#endif
+#define NV12EQ_STR2(x) #x
+#define NV12EQ_STR(x) NV12EQ_STR2(x)
+#define NV12EQ_SBASE NV12EQ_STR(NV12EQ_CLAHE_SMEM_BASE)   // the immediate of every [reg + imm] shared access below
+constexpr int kCT = 256;                        // threads of one work group
+constexpr int kGroups = 2;                      // work groups per CTA (one per half of the table rows)
+constexpr int kBlockThreads = kCT * kGroups;
 constexpr int kCWarps = kCT / 32;
 constexpr int kClaheCtas = NV12EQ_CLAHE_CTAS;   // CTAs per SM the kernel is built for
-constexpr int kRowShift = NV12EQ_CLAHE_ROWSHIFT;
-constexpr int kRowBytes = 1 << kRowShift;       // bytes per table row: hist[bin][32 lanes] u32 (128 B used) or table[v][reps] uint2
-constexpr int kCellReps = kRowBytes / 8;        // 8-byte replicas of a cell table entry (32 or 16: conflict-free per half-warp)
-static_assert(kRowShift == 7 || kRowShift == 8, "table rows are 128 or 256 bytes");
-static_assert(kCT % 256 == 0 && kCT >= 256 && kCT <= 1024, "table build maps threads to the 256 values");
+constexpr uint32_t kSmemBase = NV12EQ_CLAHE_SMEM_BASE;
+constexpr int kRowShift = 8;
+constexpr int kRowBytes = 1 << kRowShift;       // pitch of a table row
+constexpr int kHalfBytes = kRowBytes / kGroups; // a group's part of every row
+constexpr int kCellReps = 16;                   // 8-byte replicas of a cell table entry (conflict-free per half-warp)
 constexpr int kRowTableBytes = 256 * kRowBytes;
-constexpr int kRingDepth = 8;                   // pixel rows in flight per thread in the cell loop (power of two)
-constexpr int kTileDepth = 4;                   // 16-byte tile row pieces in flight per thread in the tile loop
-constexpr int kRingBytes = kRingDepth * kCT * 8;
-static_assert(kTileDepth * kCT * 16 <= kRingBytes, "tile ring must fit");
-constexpr int kClaheSmemBytes = kRowTableBytes + kRingBytes;  // dynamic shared memory of clahe_kernel
+constexpr int kRingBytesPerThread = 64;         // cp.async ring of the cell loop: 4 x 16 or 8 x 8 bytes in flight per thread
+constexpr int kIterDepth = NV12EQ_CLAHE_DEPTH;  // row iterations in flight per thread in the cell loop
+#ifndef NV12EQ_CLAHE_G16
+#define NV12EQ_CLAHE_G16 1
+#endif
+constexpr bool kUseG16 = NV12EQ_CLAHE_G16 != 0;   // 16 pixels per thread-row where alignment allows (32 registers of x weights); else 8 pixels x 2 rows
+// shared memory map (byte offsets from the start of nv12eq_smem_rows); per-group areas are indexed by the group
+constexpr int kRingOff = kRowTableBytes;                                   // [kGroups][kCT * kRingBytesPerThread]
+constexpr int kRingGroupBytes = kCT * kRingBytesPerThread;
+constexpr int kYwOff = kRingOff + kGroups * kRingGroupBytes;               // [kGroups][kMaxCellRows] float2 (ya1, ya)
+constexpr int kScratchOff = kYwOff + kGroups * kMaxCellRows * 8;           // [kGroups][2 * kCWarps] words of the LUT build
+constexpr int kMiscOff = kScratchOff + kGroups * 2 * kCWarps * 4;          // [kGroups][kMiscWords]
+constexpr int kMiscWords = 8;                                              // ticket slots [2], look-ahead flags [2], flag, last
+constexpr int kClaheSmemBytes = kMiscOff + kGroups * kMiscWords * 4;       // dynamic shared memory of clahe_kernel
 
 struct ClaheParams {
     const uint8_t* in;
@@ -85,12 +107,15 @@ struct ClaheParams {
     int nxc, nyc;      // interpolation cells per axis
     const int4* xcells;  // [nxc] {x0, x1, tx1, tx2}
     const int4* ycells;  // [nyc] {y0, y1, ty1, ty2}
+    int cells_in_params; // nxc, nyc <= kParamCells: the tables below are used (a constant-bank read instead of a global load
+                         // at the head of every cell item's dependency chain)
+    int4 xc_small[kParamCells], yc_small[kParamCells];
     int uv_chunks;     // chroma items per frame (0 when nothing to do)
     unsigned long long uv_bytes, uv_chunk;  // flat
     int uv_rows_chunk;                      // strided
     int lag;
     uint8_t* luts;         // [n_frames][tx*ty][256]
-    uint32_t* tiles_done;  // [n_frames] self-cleaned
+    uint32_t* tiles_done;  // [n_frames] published tile LUTs per frame; self-cleaned
     uint32_t* ticket;      // [1] self-cleaned
     uint32_t* status;      // [1]
     unsigned long long* trace;  // optional [items][4] (developer tool)
@@ -110,66 +135,208 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-// ---- 256-byte-row shared tables -----------------------------------------------------------------------------
-// Row v of the table starts at tbase + v*kRowBytes.  `lane_off` is this lane's byte offset inside a row.  With 256-byte
-// rows it lives in byte 0 of the register and byte K of a packed pixel word goes to byte 1: one PRMT = the whole offset.
-// With 128-byte rows it is PRMT (extract) + one multiply-add onto the loop-invariant tbase + lane_off.
-template <int K>
-__device__ __forceinline__ uint32_t row_addr(uint32_t w, uint32_t tbase, uint32_t lane_off) {
-    if (kRowShift == 8) return tbase + __byte_perm(w, lane_off, 0x5504u | (K << 4));
-    return (tbase + lane_off) + (byte_of<K>(w) << kRowShift);
+// ---- shared memory accessed as [register + kSmemBase] ----------------------------------------------------------
+// `off` is a byte offset from the start of nv12eq_smem_rows.
+#ifdef NV12EQ_CLAHE_ATOMS_ADD
+// variant: the increment in a register (SASS ATOMS.ADD instead of ATOMS.POPC.INC)
+__device__ __forceinline__ void red_inc_rel(uint32_t off) {
+    uint32_t one;
+    asm("mov.u32 %0, %%nctaid.y;" : "=r"(one));   // 1 for this kernel's 1-D grid, unknown to ptxas; not volatile: hoisted out of the loops
+    asm volatile("red.shared.add.u32 [%0+" NV12EQ_SBASE "], %1;" ::"r"(off), "r"(one) : "memory");
 }
+#else
+__device__ __forceinline__ void red_inc_rel(uint32_t off) { asm volatile("red.shared.add.u32 [%0+" NV12EQ_SBASE "], 1;" ::"r"(off) : "memory"); }
+#endif
+__device__ __forceinline__ uint2 lds64_rel(uint32_t off) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+" NV12EQ_SBASE "];" : "=r"(v.x), "=r"(v.y) : "r"(off));
+    return v;
+}
+__device__ __forceinline__ uint64_t lds_b64_rel(uint32_t off) {
+    uint64_t v;
+    asm volatile("ld.shared.b64 %0, [%1+" NV12EQ_SBASE "];" : "=l"(v) : "r"(off));
+    return v;
+}
+__device__ __forceinline__ int4 lds128_rel(uint32_t off) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4+" NV12EQ_SBASE "];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(off));
+    return v;
+}
+__device__ __forceinline__ void cp_async8_rel(uint32_t off, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0+" NV12EQ_SBASE "], [%1], 8;" ::"r"(off), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16_rel(uint32_t off, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0+" NV12EQ_SBASE "], [%1], 16;" ::"r"(off), "l"(g) : "memory");
+}
+// ---- 256-byte-pitch shared tables ------------------------------------------------------------------------------
+// Row v of the table is at byte offset v << 8.  `lane_off` is this lane's byte offset inside a row (< 128, bytes 1..3 of
+// the register zero): byte K of a packed pixel word goes to byte 1, the lane offset stays in byte 0 -- one PRMT is the
+// whole offset, the base is the instruction's immediate.
+template <int K>
+__device__ __forceinline__ uint32_t row_off(uint32_t w, uint32_t lane_off) { return __byte_perm(w, lane_off, 0x5504u | (K << 4)); }
 
 // histogram rows: hist[bin][lane] u32 in the first 128 bytes of row `bin`
-__device__ __forceinline__ void hist256_byte(uint32_t v, uint32_t tbase, uint32_t lane4) { red_shared_inc(tbase + (v << kRowShift) + lane4); }
-__device__ __forceinline__ void hist256_word(uint32_t w, uint32_t tbase, uint32_t lane4) {
-    red_shared_inc(row_addr<0>(w, tbase, lane4));
-    red_shared_inc(row_addr<1>(w, tbase, lane4));
-    red_shared_inc(row_addr<2>(w, tbase, lane4));
-    red_shared_inc(row_addr<3>(w, tbase, lane4));
+__device__ __forceinline__ void hist256_byte(uint32_t v, uint32_t lane4) { red_inc_rel((v << kRowShift) + lane4); }
+__device__ __forceinline__ void hist256_word(uint32_t w, uint32_t lane4) {
+    red_inc_rel(row_off<0>(w, lane4));
+    red_inc_rel(row_off<1>(w, lane4));
+    red_inc_rel(row_off<2>(w, lane4));
+    red_inc_rel(row_off<3>(w, lane4));
 }
-__device__ __forceinline__ void hist256_vec(int4 v, uint32_t tbase, uint32_t lane4) {
-    hist256_word((uint32_t)v.x, tbase, lane4);
-    hist256_word((uint32_t)v.y, tbase, lane4);
-    hist256_word((uint32_t)v.z, tbase, lane4);
-    hist256_word((uint32_t)v.w, tbase, lane4);
+__device__ __forceinline__ void hist256_vec(int4 v, uint32_t lane4) {
+    hist256_word((uint32_t)v.x, lane4);
+    hist256_word((uint32_t)v.y, lane4);
+    hist256_word((uint32_t)v.z, lane4);
+    hist256_word((uint32_t)v.w, lane4);
 }
 // n contiguous bytes by one warp (general tile path): 16-byte vectors where alignment allows, bytes elsewhere
-__device__ __forceinline__ void hist256_span_warp(const uint8_t* __restrict__ p, int n, int lane, uint32_t tbase, uint32_t lane4,
-                                                  uint64_t pol) {
+__device__ __forceinline__ void hist256_span_warp(const uint8_t* __restrict__ p, int n, int lane, uint32_t lane4, uint64_t pol) {
     const int mis = (int)((16 - ((uintptr_t)p & 15)) & 15);
     const int head = min(mis, n);
-    for (int i = lane; i < head; i += 32) hist256_byte(p[i], tbase, lane4);
+    for (int i = lane; i < head; i += 32) hist256_byte(p[i], lane4);
     const int nvec = (n - head) >> 4;
     const uint8_t* v = p + head;
-    for (int i = lane; i < nvec; i += 32) hist256_vec(ldg128_hint(v + (size_t)i * 16, pol), tbase, lane4);
-    for (int i = head + (nvec << 4) + lane; i < n; i += 32) hist256_byte(p[i], tbase, lane4);
+    for (int i = lane; i < nvec; i += 32) hist256_vec(ldg128_hint(v + (size_t)i * 16, pol), lane4);
+    for (int i = head + (nvec << 4) + lane; i < n; i += 32) hist256_byte(p[i], lane4);
 }
-__device__ __forceinline__ void hist256_zero(uint32_t* tab) {
+// named barrier of one work group (ids 1..kGroups; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kCT) : "memory"); }
+
+// `half` = rows + group * kHalfBytes: the group's 128 bytes of every row
+__device__ __forceinline__ void hist256_zero(uint8_t* half, int tid) {
     const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < 2048 / kCT; ++k) {
-        const int i = threadIdx.x + k * kCT;  // 16-byte slot i of the 128 counter bytes of every row: row i>>3, column i&7
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(tab) + (i >> 3) * kRowBytes + (i & 7) * 16) = z;
+        const int i = tid + k * kCT;  // 16-byte slot i of the 128 counter bytes of every row: row i>>3, column i&7
+        *reinterpret_cast<uint4*>(half + (i >> 3) * kRowBytes + (i & 7) * 16) = z;
     }
 }
-__device__ __forceinline__ uint32_t hist256_row_sum(const uint32_t* tab, int bin) {
-    const uint8_t* row = reinterpret_cast<const uint8_t*>(tab) + bin * kRowBytes;
+__device__ __forceinline__ uint32_t hist256_row_sum(const uint8_t* half, int bin) {
+    const uint8_t* row = half + bin * kRowBytes;
     uint32_t s = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const uint4 q = *reinterpret_cast<const uint4*>(row + ((j + bin) & 7) * 16);
+        const uint4 q = *reinterpret_cast<const uint4*>(row + ((j + bin) & 7) * 16);   // 256-byte pitch: every row starts in bank 0, rotate by the row
         s += q.x + q.y + q.z + q.w;
     }
     return s;
 }
+
+__device__ __forceinline__ int4 cell_x(const ClaheParams& p, int cx) { return p.cells_in_params ? p.xc_small[cx] : p.xcells[cx]; }
+__device__ __forceinline__ int4 cell_y(const ClaheParams& p, int cy) { return p.cells_in_params ? p.yc_small[cy] : p.ycells[cy]; }
+
+// Work tickets of one work group (see TicketQueue in common.cuh for the protocol): the group's thread 0 draws the next ticket
+// shortly before the end of an item and publishes it through the group's shared slots at the group's barrier.
+// Look-ahead: when the ticket just drawn is a cell item, thread 0 also reads (acquire) the tile counter of that item's frame.
+// In steady state the tiles are long complete, so the next item starts with the answer in hand: no polling round trip and no
+// extra barrier at the head of the cell item's dependency chain.
+struct GroupTickets {
+    uint32_t* counter;   // [0] ticket, [2] exit count  (misc workspace words)
+    uint32_t* slots;     // shared uint32[4] of this group: tickets [2], look-ahead flags [2]
+    int tid, bar;
+    // decoding of a ticket (same values the kernel uses)
+    const ClaheParams& p;
+    uint32_t total_items, per_slot;
+    int T, I;
+    uint32_t pending, pending_ready;
+    uint32_t round;
+    bool drawn;          // thread 0: the next ticket has been drawn
+    __device__ __forceinline__ void start() {
+        round = 0;
+        drawn = false;
+        pending_ready = 0;
+        if (tid == 0) {
+            slots[0] = atomicAdd(counter, 1u);
+            slots[2] = 0;
+        }
+        group_sync(bar);
+    }
+    __device__ __forceinline__ uint32_t current() const { return slots[round & 1]; }
+    __device__ __forceinline__ bool current_ready() const { return slots[2 + (round & 1)] != 0; }
+    __device__ __forceinline__ void prefetch() {   // thread 0 only (other threads: no-op); idempotent within an item
+        if (tid == 0 && !drawn) {
+            pending = atomicAdd(counter, 1u);
+            drawn = true;
+            pending_ready = 0;
+            if (pending < total_items) {
+                const uint32_t g = p.slot_magic ? __umulhi(pending, p.slot_magic) : pending / per_slot;
+                const int r = (int)(pending - g * per_slot), f = (int)g - p.lag;
+                if (r >= T && r < T + I && f >= 0) pending_ready = ld_acquire_u32(p.tiles_done + f) >= (uint32_t)T;
+            }
+        }
+    }
+    __device__ __forceinline__ void advance() {    // also the end-of-item barrier that protects the group's tables
+        prefetch();
+        if (tid == 0) {
+            slots[(round + 1) & 1] = pending;
+            slots[2 + ((round + 1) & 1)] = pending_ready;
+        }
+        drawn = false;
+        ++round;
+        group_sync(bar);
+    }
+    // Call once, by all threads of the group, when it has no more work.  True (to every thread) in the last group of the grid.
+    __device__ __forceinline__ bool finish(int* flag) {
+        group_sync(bar);
+        if (tid == 0) {
+            __threadfence();
+            const bool last = atomicAdd(counter + 2, 1u) == gridDim.x * kGroups - 1;
+            if (last) {
+                counter[0] = 0;
+                counter[2] = 0;
+            }
+            *flag = last;
+        }
+        group_sync(bar);
+        return *flag != 0;
+    }
+};
+
+// One tile's pixel rows -> histogram.  Threads form a (rows per pass x 16-byte pieces per row) grid over the tile; a thread
+// walks down its column of pieces, staged through its slots of the group's cp.async ring (kRingBytesPerThread / 16 - 1 pieces
+// in flight without holding registers).  Loading the pieces straight into registers instead (256-bit or 128-bit LDG with
+// L2::evict_last, four deep) measured 5 % slower per frame on B200 (profiles/r02_clahe_notes.md): the tile pass is bound by the
+// shared-atomic rate (~16 lanes per clock per SM), and what matters beside it is that waiting warps cost no registers.
+struct TileRowsRing {
+    static constexpr int D = kRingBytesPerThread / 16;
+    static constexpr uint32_t kSlotStride = kCT * 16;
+    const uint8_t* pn;
+    size_t rstep;
+    int nrows;
+    uint32_t ring0;
+    __device__ __forceinline__ void start(const uint8_t* __restrict__ ptr, size_t rstep_, int nrows_, int tid, int group) {
+        rstep = rstep_; nrows = nrows_; ring0 = (uint32_t)(kRingOff + group * kRingGroupBytes + tid * 16);
+#pragma unroll
+        for (int j = 0; j < D - 1; ++j) {
+            if (j < nrows) cp_async16_rel(ring0 + (uint32_t)j * kSlotStride, ptr + (size_t)j * rstep);
+            cp_async_commit();
+        }
+        pn = ptr + (size_t)(D - 1) * rstep;
+    }
+    __device__ __forceinline__ void run(uint32_t lane4, GroupTickets& q) {
+#pragma unroll 1
+        for (int i0 = 0; i0 < nrows; i0 += D) {
+            if (i0 + 2 * D >= nrows) q.prefetch();
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (i0 + j < nrows) {
+                    if (i0 + j + D - 1 < nrows) cp_async16_rel(ring0 + (uint32_t)((j + D - 1) % D) * kSlotStride, pn);
+                    cp_async_commit();
+                    cp_async_wait<D - 1>();
+                    hist256_vec(lds128_rel(ring0 + (uint32_t)j * kSlotStride), lane4);
+                    pn += rstep;
+                }
+            }
+        }
+    }
+};
 
 // Tile histogram -> clip -> redistribute -> scan -> LUT bytes (global), by the whole CTA: thread t < 256 owns bin t
 // (count = its histogram value).  The per-bin work (clip, residual test, conversion) runs 256 wide and the two reductions
 // cost one barrier each; a single-warp version kept the other warps of the CTA waiting ~1 us per tile.
 // s_scratch: 2 * kCWarps words.
 __device__ __forceinline__ void clahe_tile_lut_block(uint32_t count, int clip_limit, float lut_scale, uint8_t* __restrict__ glut,
-                                                     uint32_t* s_scratch, int tid) {
+                                                     uint32_t* s_scratch, int tid, int bar) {
     const int lane = tid & 31, warp = tid >> 5;
     int h = tid < 256 ? (int)count : 0;
     if (clip_limit > 0) {   // uniform over the CTA
@@ -178,7 +345,7 @@ __device__ __forceinline__ void clahe_tile_lut_block(uint32_t count, int clip_li
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) excess += __shfl_xor_sync(0xffffffffu, excess, d);
         if (lane == 0) s_scratch[warp] = (uint32_t)excess;
-        __syncthreads();
+        group_sync(bar);
         int clipped = 0;
 #pragma unroll
         for (int w = 0; w < kCWarps; ++w) clipped += (int)s_scratch[w];
@@ -194,7 +361,7 @@ __device__ __forceinline__ void clahe_tile_lut_block(uint32_t count, int clip_li
     }
     const uint32_t incl = warp_incl_scan((uint32_t)h, lane);
     if (lane == 31) s_scratch[kCWarps + warp] = incl;
-    __syncthreads();
+    group_sync(bar);
     uint32_t run = incl;
 #pragma unroll
     for (int w = 0; w < kCWarps; ++w)
@@ -225,8 +392,8 @@ __device__ __forceinline__ float clahe_blend_res(uint2 e, float xa, float xa1, u
     return __fadd_rn(r0, r1);
 }
 template <int K>
-__device__ __forceinline__ float clahe_blend_px(uint32_t w, uint32_t tbase, uint32_t lane8, float xa, float xa1, uint64_t yw) {
-    return clahe_blend_res(lds_u64(row_addr<K>(w, tbase, lane8)), xa, xa1, yw);
+__device__ __forceinline__ float clahe_blend_px(uint32_t w, uint32_t lane8, float xa, float xa1, uint64_t yw) {
+    return clahe_blend_res(lds64_rel(row_off<K>(w, lane8)), xa, xa1, yw);
 }
 __device__ __forceinline__ void round_pair(float a, float b, uint32_t& oa, uint32_t& ob) {
     unpack_u2(add_f2(pack_f2(a, b), pack_f2(12582912.0f, 12582912.0f)), oa, ob);
@@ -237,18 +404,15 @@ __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint3
 }
 // eight horizontally adjacent pixels (two packed words) -> two packed output words
 __device__ __forceinline__ uint2 clahe_blend_8(uint2 px, uint32_t lane8, const float* xa, const float* xa1, uint64_t yw) {
-    // re-read the table base here: a fresh uniform value lets ptxas address the gathers as [R + UR] instead of adding
-    // a base held in a vector register to every offset
-    const uint32_t tbase = smem_u32(nv12eq_smem_rows);
     float f[8];
-    f[0] = clahe_blend_px<0>(px.x, tbase, lane8, xa[0], xa1[0], yw);
-    f[1] = clahe_blend_px<1>(px.x, tbase, lane8, xa[1], xa1[1], yw);
-    f[2] = clahe_blend_px<2>(px.x, tbase, lane8, xa[2], xa1[2], yw);
-    f[3] = clahe_blend_px<3>(px.x, tbase, lane8, xa[3], xa1[3], yw);
-    f[4] = clahe_blend_px<0>(px.y, tbase, lane8, xa[4], xa1[4], yw);
-    f[5] = clahe_blend_px<1>(px.y, tbase, lane8, xa[5], xa1[5], yw);
-    f[6] = clahe_blend_px<2>(px.y, tbase, lane8, xa[6], xa1[6], yw);
-    f[7] = clahe_blend_px<3>(px.y, tbase, lane8, xa[7], xa1[7], yw);
+    f[0] = clahe_blend_px<0>(px.x, lane8, xa[0], xa1[0], yw);
+    f[1] = clahe_blend_px<1>(px.x, lane8, xa[1], xa1[1], yw);
+    f[2] = clahe_blend_px<2>(px.x, lane8, xa[2], xa1[2], yw);
+    f[3] = clahe_blend_px<3>(px.x, lane8, xa[3], xa1[3], yw);
+    f[4] = clahe_blend_px<0>(px.y, lane8, xa[4], xa1[4], yw);
+    f[5] = clahe_blend_px<1>(px.y, lane8, xa[5], xa1[5], yw);
+    f[6] = clahe_blend_px<2>(px.y, lane8, xa[6], xa1[6], yw);
+    f[7] = clahe_blend_px<3>(px.y, lane8, xa[7], xa1[7], yw);
     uint32_t o[8];
 #pragma unroll
     for (int k = 0; k < 8; k += 2) round_pair(f[k], f[k + 1], o[k], o[k + 1]);
@@ -261,65 +425,85 @@ __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float&
     a = __fsub_rn(f, t1);
     a1 = __fsub_rn(1.0f, a);
 }
-// keeps a value in its register: stops the compiler from re-deriving xa1 = 1 - xa inside the pixel loop
-__device__ __forceinline__ void pin_register(float& v) { asm volatile("" : "+f"(v)); }
 
-// The rows of one thread inside a cell: G (8 or 16) horizontally adjacent pixels per row, rows tr, tr + rpp, ...
-// Thread-private ring of D G-byte slots in shared memory, filled with cp.async: the rows D-1 ahead are in flight
-// (about 50 KB per SM) without holding registers, and since a thread only ever reads its own slots no barrier is
-// involved.  The row loop is unrolled by the ring depth, so every ring slot is a compile-time offset.  Thread 0
-// (tr == 0, the most rows) draws the next ticket at the start of the last round, which hides the atomic's round trip.
-// G = 16 halves the per-row overhead (ring, pointers, y weights, loop) per pixel; it needs 32 registers of x weights.
-template <int G>
+// The rows of one thread inside a cell: G (8 or 16) horizontally adjacent pixels per row, rows tr, tr + rpp, ...; R of
+// them per loop iteration (the x weights are shared by all rows, so R = 2 halves the per-iteration overhead per pixel
+// without more weight registers -- what the 8-pixel path of small cells needs).  Thread-private ring of D * R G-byte slots
+// in the spare half of the thread's own table row, filled with cp.async: the rows of D - 1 iterations ahead are in flight
+// without holding registers, and since a thread only ever reads its own slots no barrier is involved.  The loop is unrolled
+// by D, so every ring slot is a compile-time offset.  Thread 0 (tr == 0, the most rows) draws the next ticket at the start of
+// the last round, which hides the atomic's round trip.
+template <int G, int R>
 struct CellRows {
-    static constexpr int D = (G == 16) ? kRingDepth / 2 : kRingDepth;   // same ring bytes either way
-    static constexpr uint32_t kSlot = kCT * G;
+    static constexpr int D = kIterDepth;
+    static_assert(D * R * G <= kRingBytesPerThread, "ring must fit the thread's slots");
     float xa[G], xa1[G];
     const uint8_t* spn;
     uint8_t* dp;
     size_t rstep;
-    uint32_t ring0, yw_addr, yw_step;
+    uint32_t ring0, yw_off, yw_step;
     int nrows;
 
-    __device__ __forceinline__ void issue(uint32_t slot, const uint8_t* g) const {
-        if (G == 16) cp_async16(ring0 + slot * kSlot, g); else cp_async8(ring0 + slot * kSlot, g);
+    // Slot j of thread t is at ring0 + j * kSlotStride with ring0 = group ring + t * G: consecutive threads sit G bytes
+    // apart, so a warp-wide access is one contiguous span (no bank conflicts) and every slot is the instruction's immediate.
+    static constexpr uint32_t kSlotStride = kCT * G;
+    static __device__ __forceinline__ uint32_t ring_base(int tid, int group) {
+        return (uint32_t)(kRingOff + group * kRingGroupBytes + tid * G);
     }
-    // Everything that does not depend on the tile LUTs: x weights and the first D-1 rows of the ring.  Called BEFORE the
-    // dependency wait and the table build, so the pixel loads are in flight while the CTA waits for / packs the LUTs.
-    __device__ __forceinline__ void start(const uint8_t* sp, uint8_t* dp_, size_t rstep_, int nrows_, int xg, float inv_tw, uint32_t ring0_,
-                                          uint32_t yw_addr_, uint32_t yw_step_) {
-        dp = dp_; rstep = rstep_; nrows = nrows_; ring0 = ring0_; yw_addr = yw_addr_; yw_step = yw_step_;
+    __device__ __forceinline__ void issue(int slot, const uint8_t* g) const {
+        if (G == 16) cp_async16_rel(ring0 + (uint32_t)slot * kSlotStride, g); else cp_async8_rel(ring0 + (uint32_t)slot * kSlotStride, g);
+    }
+    // Everything that does not depend on the tile LUTs: x weights and the first D-1 iterations of the ring.  Called BEFORE
+    // the dependency wait and the table build, so the pixel loads are in flight while the CTA waits for / packs the LUTs.
+    __device__ __forceinline__ void start(const uint8_t* sp, uint8_t* dp_, size_t rstep_, int nrows_, int xg, float inv_tw, int tid, int group,
+                                          uint32_t yw_off_, uint32_t yw_step_) {
+        dp = dp_; rstep = rstep_; nrows = nrows_; ring0 = ring_base(tid, group); yw_off = yw_off_; yw_step = yw_step_;
 #pragma unroll
-        for (int k = 0; k < G; ++k) axis_weight(xg + k, inv_tw, xa[k], xa1[k]);
+        for (int k = 0; k < G; ++k) {
+            axis_weight(xg + k, inv_tw, xa[k], xa1[k]);
+#ifdef NV12EQ_CLAHE_PIN
+            asm volatile("" : "+f"(xa1[k]));   // keep 1 - xa in its register: stops the compiler re-deriving it per pixel
+#endif
+        }
 #pragma unroll
         for (int j = 0; j < D - 1; ++j) {
-            if (j < nrows) issue((uint32_t)j, sp + (size_t)j * rstep);
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (j * R + r < nrows) issue(j * R + r, sp + (size_t)(j * R + r) * rstep);
             cp_async_commit();
         }
-        spn = sp + (size_t)(D - 1) * rstep;
+        spn = sp + (size_t)((D - 1) * R) * rstep;
     }
-    __device__ __forceinline__ void run(TicketQueue& q, uint32_t lane8) {
+    __device__ __forceinline__ void run(GroupTickets& q, uint32_t lane8) {
 #pragma unroll 1
-        for (int i0 = 0; i0 < nrows; i0 += D) {
-            if (i0 + D >= nrows) q.prefetch();
+        for (int i0 = 0; i0 < nrows; i0 += D * R) {
+            if (i0 + D * R >= nrows) q.prefetch();
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                const int i = i0 + j;
+                const int i = i0 + j * R;
                 if (i < nrows) {
-                    if (i + D - 1 < nrows) issue((uint32_t)((j + D - 1) % D), spn);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (i + (D - 1) * R + r < nrows) issue(((j + D - 1) % D) * R + r, spn + (size_t)r * rstep);
                     cp_async_commit();
                     cp_async_wait<D - 1>();
-                    const uint64_t yw = lds_b64(yw_addr);
-                    if (G == 16) {
-                        const int4 px = lds_s4(ring0 + (uint32_t)j * kSlot);
-                        const uint2 o0 = clahe_blend_8(make_uint2((uint32_t)px.x, (uint32_t)px.y), lane8, xa, xa1, yw);
-                        const uint2 o1 = clahe_blend_8(make_uint2((uint32_t)px.z, (uint32_t)px.w), lane8, xa + 8 * (G / 16), xa1 + 8 * (G / 16), yw);
-                        __stcs(reinterpret_cast<uint4*>(dp), make_uint4(o0.x, o0.y, o1.x, o1.y));
-                    } else {
-                        const uint2 px = lds_u64(ring0 + (uint32_t)j * kSlot);
-                        __stcs(reinterpret_cast<uint2*>(dp), clahe_blend_8(px, lane8, xa, xa1, yw));
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (r == 0 || i + r < nrows) {
+                            const uint64_t yw = lds_b64_rel(yw_off + (uint32_t)r * yw_step);
+                            uint8_t* d = dp + (size_t)r * rstep;
+                            if (G == 16) {
+                                const int4 px = lds128_rel(ring0 + (uint32_t)(j * R + r) * kSlotStride);
+                                const uint2 o0 = clahe_blend_8(make_uint2((uint32_t)px.x, (uint32_t)px.y), lane8, xa, xa1, yw);
+                                const uint2 o1 = clahe_blend_8(make_uint2((uint32_t)px.z, (uint32_t)px.w), lane8, xa + 8 * (G / 16), xa1 + 8 * (G / 16), yw);
+                                __stcs(reinterpret_cast<uint4*>(d), make_uint4(o0.x, o0.y, o1.x, o1.y));
+                            } else {
+                                const uint2 px = lds64_rel(ring0 + (uint32_t)(j * R + r) * kSlotStride);
+                                __stcs(reinterpret_cast<uint2*>(d), clahe_blend_8(px, lane8, xa, xa1, yw));
+                            }
+                        }
                     }
-                    spn += rstep; dp += rstep; yw_addr += yw_step;
+                    spn += (size_t)R * rstep; dp += (size_t)R * rstep; yw_off += (uint32_t)R * yw_step;
                 }
             }
         }
@@ -327,34 +511,53 @@ struct CellRows {
 };
 
 template <int MIN_CTAS>
-__global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams p) {
-    uint32_t* const smem_rows = nv12eq_smem_rows;  // 64 KB of 256-byte rows: hist[bin][32] (tile items) / table[v][32] (cells); then the ring
-    __shared__ uint32_t s_bins[256];
-    __shared__ __align__(8) float2 s_yw[kMaxCellRows];  // (ya1, ya) of the rows of the current cell
-    __shared__ uint32_t s_ticket[2];
-    __shared__ int s_flag;
+__global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const ClaheParams p) {
+    uint8_t* const rows = reinterpret_cast<uint8_t*>(nv12eq_smem_rows);   // see the shared memory map above
+    const int group = threadIdx.x / kCT, tid = threadIdx.x - group * kCT, lane = tid & 31, warp = tid >> 5;
+    const int bar = 1 + group;
+    uint8_t* const half = rows + group * kHalfBytes;                       // this group's 128 bytes of every table row
+    float2* const s_yw = reinterpret_cast<float2*>(rows + kYwOff) + group * kMaxCellRows;
+    uint32_t* const s_scratch = reinterpret_cast<uint32_t*>(rows + kScratchOff) + group * 2 * kCWarps;
+    uint32_t* const s_ticket = reinterpret_cast<uint32_t*>(rows + kMiscOff) + group * kMiscWords;
+    int* const s_flag = reinterpret_cast<int*>(s_ticket + 4);
+    int* const s_last = reinterpret_cast<int*>(s_ticket + 5);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (smem_u32(rows) != kSmemBase) {   // the [reg + imm] accesses below would miss the tables: refuse loudly
+        if (threadIdx.x == 0) atomicExch(p.status, 2u);
+        return;
+    }
     const int T = p.tx * p.ty;
     const int I = p.nxc * p.nyc;
     const int U = p.uv_chunks;
     const int per_slot = T + I + U;
     const uint32_t total_items = (uint32_t)(p.n_frames + p.lag) * (uint32_t)per_slot;
-    uint32_t tbase;
-    asm("mov.u32 %0, nv12eq_smem_rows;" : "=r"(tbase));
-    const uint32_t rbase = tbase + kRowTableBytes;  // cp.async ring of the cell loop
-    const uint32_t lane4 = (uint32_t)lane * 4u, lane8 = (uint32_t)(lane & (kCellReps - 1)) * 8u;
+    const uint32_t lane4 = (uint32_t)(group * kHalfBytes + lane * 4);                        // hist column of this lane
+    const uint32_t lane8 = (uint32_t)(group * kHalfBytes + (lane & (kCellReps - 1)) * 8);    // cell table replica of this lane
+    const uint32_t yw_base = (uint32_t)(kYwOff + group * kMaxCellRows * 8);
 
-    TicketQueue q{p.ticket, s_ticket, 0u, 0u, false};
+    GroupTickets q{p.ticket, s_ticket, tid, bar, p, total_items, (uint32_t)per_slot, T, I, 0u, 0u, 0u, false};
     q.start();
+    int publish = -1;   // thread 0: frame whose tile counter still has to be bumped for the tile item just finished
+    // The LUT bytes of a tile item are stored by all threads before the item's closing barrier (q.advance); thread 0 then fences
+    // and counts the tile at the top of the next iteration (the cooperative-groups grid-sync pattern: barrier, then one thread
+    // fences and signals), while the other warps already work on the next item.
+    // (Per-TILE flags, so that a cell only waits for its own four tiles, measured 2 % slower: four flag reads per look-ahead.)
+    auto publish_tile = [&]() {
+        if (tid == 0 && publish >= 0) {
+            __threadfence();
+            atomicAdd(p.tiles_done + publish, 1u);
+            publish = -1;
+        }
+    };
     for (;;) {
         const uint32_t item = q.current();
+        publish_tile();
         if (item >= total_items) break;
         // item = g * per_slot + r; the host supplies floor(2^32 / per_slot) + 1 when that multiplier divides exactly
         const int g = p.slot_magic ? (int)__umulhi(item, p.slot_magic) : (int)(item / (uint32_t)per_slot);
         const int r = (int)(item - (uint32_t)g * (uint32_t)per_slot);
         const int f = g - p.lag;
-        const ItemTrace tr_{p.trace};
+        const ItemTrace tr_{p.trace, tid};
         tr_.mark(item, 0);
         tr_.mark(item, 1);
         tr_.kind(item, r < T ? 1u : (r < T + I ? 2u : 3u));
@@ -366,64 +569,43 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 const int tyi = small_div(r, p.tx), txi = r - tyi * p.tx;
                 const int x0 = txi * p.tw, y0 = tyi * p.th;
                 const uint64_t keep = l2_policy_evict_last();
-                const bool vec_ok = !(p.debug_skip & 1) && !p.padded && (p.tw & 15) == 0 && (p.stride & 15) == 0 &&
-                                    (((uintptr_t)y + (uintptr_t)x0) & 15) == 0 && (p.tw >> 4) <= kCT;
-                // threads form a (rows_per_pass x vectors_per_row) grid over the tile.  Every thread keeps
-                // kTileDepth-1 of its 16-byte row pieces in flight through a private cp.async ring; the first ones are issued
-                // before the table is zeroed so that their latency overlaps the set-up of the item.
-                const int vpr = vec_ok ? (p.tw >> 4) : 1;
+                const uintptr_t align_or = (uintptr_t)y + (uintptr_t)x0;
+                const bool vec16 = !(p.debug_skip & 1) && !p.padded && (p.tw & 15) == 0 && (p.stride & 15) == 0 && (align_or & 15) == 0 &&
+                                   (p.tw >> 4) <= kCT;
+                                // threads form a (rows_per_pass x vectors_per_row) grid over the tile
+                const int vpr = vec16 ? (p.tw >> 4) : 1;
                 const int rpp = small_div(kCT, vpr);
                 const int tr = small_div(tid, vpr), tc = tid - tr * vpr;
-                const int nrows = (vec_ok && tr < rpp && tr < p.th) ? small_div(p.th - tr + rpp - 1, rpp) : 0;
+                const int nrows = (vec16 && tr < rpp && tr < p.th) ? small_div(p.th - tr + rpp - 1, rpp) : 0;
                 const uint8_t* ptr = y + (size_t)(y0 + tr) * p.stride + x0 + tc * 16;
                 const size_t rstep = (size_t)rpp * p.stride;
-                const uint32_t ring0 = rbase + (uint32_t)tid * 16u;
-                constexpr uint32_t kSlot = kCT * 16u;
-                if (vec_ok) {
-#pragma unroll
-                    for (int j = 0; j < kTileDepth - 1; ++j) {
-                        if (j < nrows) cp_async16(ring0 + (uint32_t)j * kSlot, ptr + (size_t)j * rstep);
-                        cp_async_commit();
-                    }
-                }
-                hist256_zero(smem_rows);
-                __syncthreads();
                 if (p.debug_skip & 1) {
-                } else if (vec_ok) {
-                    const uint8_t* pn = ptr + (size_t)(kTileDepth - 1) * rstep;
-                    // unrolled by the ring depth: every slot is a compile-time offset
-#pragma unroll 1
-                    for (int i0 = 0; i0 < nrows; i0 += kTileDepth) {
-#pragma unroll
-                        for (int j = 0; j < kTileDepth; ++j) {
-                            const int i = i0 + j;
-                            if (i < nrows) {
-                                if (i + kTileDepth - 1 < nrows) cp_async16(ring0 + (uint32_t)((j + kTileDepth - 1) % kTileDepth) * kSlot, pn);
-                                cp_async_commit();
-                                cp_async_wait<kTileDepth - 1>();
-                                hist256_vec(lds_s4(ring0 + (uint32_t)j * kSlot), tbase, lane4);
-                                pn += rstep;
-                            }
-                        }
-                    }
+                    hist256_zero(half, tid);
+                    group_sync(bar);
+                } else if (vec16) {
+                    TileRowsRing t;
+                    t.start(ptr, rstep, nrows, tid, group);   // the first loads leave before the table is zeroed
+                    hist256_zero(half, tid);
+                    group_sync(bar);
+                    t.run(lane4, q);
                 } else {
+                    hist256_zero(half, tid);
+                    group_sync(bar);
                     // general path: one warp per tile row, byte spans inside the image, reflected reads outside
                     for (int row = warp; row < p.th; row += kCWarps) {
                         const uint8_t* src_row = y + (size_t)reflect101(y0 + row, p.h) * p.stride;
                         const int xin = min(x0 + p.tw, p.w);  // end of the in-image part
-                        if (x0 < xin) hist256_span_warp(src_row + x0, xin - x0, lane, tbase, lane4, keep);
+                        if (x0 < xin) hist256_span_warp(src_row + x0, xin - x0, lane, lane4, keep);
                         for (int x = max(x0, p.w) + lane; x < x0 + p.tw; x += 32)
-                            hist256_byte(src_row[reflect101(x, p.w)], tbase, lane4);
+                            hist256_byte(src_row[reflect101(x, p.w)], lane4);
                     }
                 }
                 q.prefetch();  // the row sums and the LUT build hide the ticket round trip
-                __syncthreads();
+                group_sync(bar);
                 if (!(p.debug_skip & 8))
-                    clahe_tile_lut_block(tid < 256 ? hist256_row_sum(smem_rows, tid) : 0u, p.clip_limit, p.lut_scale,
-                                         p.luts + ((size_t)g * T + r) * 256, s_bins, tid);
-                __threadfence();   // every thread publishes its LUT byte before the tile is counted
-                __syncthreads();
-                if (tid == 0) atomicAdd(p.tiles_done + g, 1u);
+                    clahe_tile_lut_block(hist256_row_sum(half, tid), p.clip_limit, p.lut_scale, p.luts + ((size_t)g * T + r) * 256, s_scratch,
+                                         tid, bar);
+                publish = g;   // counted after the item's closing barrier, see publish_tile
             }
         } else if (f >= 0) {
             const uint8_t* src = p.in + (unsigned long long)f * p.pitch;
@@ -432,14 +614,13 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 // ------------------------- cell item: blend four tile LUTs -------------------------
                 const int ci = r - T;
                 const int cy = small_div(ci, p.nxc), cx = ci - cy * p.nxc;
-                const int4 xc = p.xcells[cx], yc = p.ycells[cy];
+                const int4 xc = cell_x(p, cx), yc = cell_y(p, cy);
                 const int cw = xc.y - xc.x, ch = yc.y - yc.x;  // cell size in pixels (ch <= kMaxCellRows)
                 // Geometry of the fast path: full groups of G = 16 (or 8) pixels, one 16- (8-) byte load / store per thread and
                 // row.  Columns left over when the cell width is not a multiple of G (and everything when alignment does not
                 // allow vector accesses) take the pixel-at-a-time path below.
-                const uint32_t ywbase = smem_u32(s_yw);
                 const uintptr_t align_or = (uintptr_t)src | (uintptr_t)dst | (uintptr_t)p.stride | (uintptr_t)xc.x;
-                const bool fast16 = ((align_or & 15) == 0) && (cw & 15) == 0 && (cw >> 4) >= 1 && (cw >> 4) <= kCT;
+                const bool fast16 = kUseG16 && ((align_or & 15) == 0) && (cw & 15) == 0 && (cw >> 4) >= 1 && (cw >> 4) <= kCT;
                 const bool fast8 = !fast16 && ((align_or & 7) == 0) && (cw >> 3) >= 1 && (cw >> 3) <= kCT;
                 const int G = fast16 ? 16 : 8;
                 const int gpr = (p.debug_skip & 2) ? 0 : (fast16 ? (cw >> 4) : (fast8 ? (cw >> 3) : 0));   // G-pixel groups per row
@@ -452,7 +633,7 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                 const int nrows = active ? small_div(ch - tr + rpp - 1, rpp) : 0;   // rows of this thread: tr, tr + rpp, ...
                 const uint8_t* sp = src + (size_t)(yc.x + tr) * p.stride + xg;
                 uint8_t* dp = dst + (size_t)(yc.x + tr) * p.stride + xg;
-                const uint32_t yw_addr = ywbase + (uint32_t)tr * 8u, yw_step = (uint32_t)rpp * 8u;
+                const uint32_t yw_off = yw_base + (uint32_t)tr * 8u, yw_step = (uint32_t)rpp * 8u;
 
                 // dependency wait + table build; everything the row loop needs that does not depend on the LUTs has been
                 // started by then (CellRows::start), so pixel loads overlap the wait and the LUT loads
@@ -463,54 +644,56 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                         axis_weight(yc.x + i, p.inv_th, ya, ya1);
                         s_yw[i] = make_float2(ya1, ya);
                     }
-                    if (tid == 0) {
-                        bool ok = true;
-                        if (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
-                            const long long t0 = clock64();
-                            unsigned ns = 64;
-                            while (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
-                                __nanosleep(ns);
-                                if (ns < 2048) ns <<= 1;
-                                if (clock64() - t0 > kSpinCycles) { ok = false; break; }
+                    if (!q.current_ready()) {   // look-ahead did not see the tiles complete: poll (rare in steady state)
+                        if (tid == 0) {
+                            bool ok = true;
+                            if (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
+                                const long long t0 = clock64();
+                                unsigned ns = 64;
+                                while (ld_acquire_u32(p.tiles_done + f) < (uint32_t)T) {
+                                    __nanosleep(ns);
+                                    if (ns < 2048) ns <<= 1;
+                                    if (clock64() - t0 > kSpinCycles) { ok = false; break; }
+                                }
                             }
+                            if (!ok) atomicExch(p.status, 1u);
+                            *s_flag = ok;
                         }
-                        if (!ok) atomicExch(p.status, 1u);
-                        s_flag = ok;
+                        group_sync(bar);
+                        if (!*s_flag) return false;
                     }
-                    __syncthreads();
-                    if (!s_flag) return false;
                     tr_.mark(item, 1);
                     if (!(p.debug_skip & 16))
-                    // pack the four LUTs: row v = replicas of {bf16 L11 | L21 << 16, bf16 L12 | L22 << 16}
+                    // pack the four LUTs: row v = 16 replicas of {bf16 L11 | L21 << 16, bf16 L12 | L22 << 16}
                     {
-                        constexpr int kShare = kCT / 256, kPer = kCellReps / kShare;
                         const uint8_t* L = p.luts + (size_t)f * T * 256;
-                        const int v = tid & 255, part = tid >> 8;
+                        const int v = tid;
                         const uint32_t l11 = __ldcg(L + (size_t)(yc.z * p.tx + xc.z) * 256 + v);
                         const uint32_t l12 = __ldcg(L + (size_t)(yc.z * p.tx + xc.w) * 256 + v);
                         const uint32_t l21 = __ldcg(L + (size_t)(yc.w * p.tx + xc.z) * 256 + v);
                         const uint32_t l22 = __ldcg(L + (size_t)(yc.w * p.tx + xc.w) * 256 + v);
-                        uint2 e;
+                        uint4 e;
                         e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l21) & 0xffff0000u);
                         e.y = (__float_as_uint((float)l12) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
-                        uint2* row = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(smem_rows) + v * kRowBytes);
+                        e.z = e.x; e.w = e.y;
+                        uint4* row = reinterpret_cast<uint4*>(half + v * kRowBytes);
 #pragma unroll
-                        for (int j = 0; j < kPer; ++j) row[(part * kPer + j + v) & (kCellReps - 1)] = e;
+                        for (int j = 0; j < kCellReps / 2; ++j) row[(j + v) & (kCellReps / 2 - 1)] = e;
                     }
-                    __syncthreads();
+                    group_sync(bar);
                     return true;
                 };
                 bool ok;
-                if (fast16) {
-                    CellRows<16> rows;
-                    rows.start(sp, dp, rstep, nrows, xg, p.inv_tw, rbase + (uint32_t)tid * 16u, yw_addr, yw_step);
+                if (fast16 && kUseG16) {
+                    CellRows<16, 1> cr;
+                    cr.start(sp, dp, rstep, nrows, xg, p.inv_tw, tid, group, yw_off, yw_step);
                     ok = wait_and_build_table();
-                    if (ok) rows.run(q, lane8);
+                    if (ok) cr.run(q, lane8);
                 } else {
-                    CellRows<8> rows;
-                    rows.start(sp, dp, rstep, nrows, xg, p.inv_tw, rbase + (uint32_t)tid * 8u, yw_addr, yw_step);
+                    CellRows<8, 2> cr;
+                    cr.start(sp, dp, rstep, nrows, xg, p.inv_tw, tid, group, yw_off, yw_step);
                     ok = wait_and_build_table();
-                    if (ok) rows.run(q, lane8);
+                    if (ok) cr.run(q, lane8);
                 }
                 if (!ok) break;
                 if (xslow < xc.y && !(p.debug_skip & 2)) {
@@ -523,7 +706,7 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                         float xa, xa1;
                         axis_weight(x, p.inv_tw, xa, xa1);
                         const uint32_t v = src[(size_t)yy * p.stride + x];
-                        const float res = clahe_blend_res(lds_u64(tbase + (v << kRowShift) + lane8), xa, xa1, lds_b64(ywbase + (uint32_t)ry * 8u));
+                        const float res = clahe_blend_res(lds64_rel((v << kRowShift) + lane8), xa, xa1, lds_b64_rel(yw_base + (uint32_t)ry * 8u));
                         dst[(size_t)yy * p.stride + x] = (uint8_t)__float_as_uint(__fadd_rn(res, 12582912.0f));
                     }
                 }
@@ -540,8 +723,8 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
                     if (copy_uv) copy_span(src + uv_off + b0, dst + uv_off + b0, (size_t)(b1 - b0), tid, kCT);
                     else if (p.uv_mode == UV_GRAY128) fill_span(dst + uv_off + b0, (size_t)(b1 - b0), tid, kCT, 128);
                 } else {
-                    const int rows = p.h / 2;
-                    const int r0 = min(c * p.uv_rows_chunk, rows), r1 = min(r0 + p.uv_rows_chunk, rows);
+                    const int rows_uv = p.h / 2;
+                    const int r0 = min(c * p.uv_rows_chunk, rows_uv), r1 = min(r0 + p.uv_rows_chunk, rows_uv);
                     for (int row = r0 + warp; row < r1; row += kCWarps) {
                         const size_t off = uv_off + (size_t)row * p.stride;
                         if (copy_uv) copy_span(src + off, dst + off, (size_t)p.w, lane, 32);
@@ -554,8 +737,9 @@ __global__ void __launch_bounds__(kCT, MIN_CTAS) clahe_kernel(const ClaheParams 
         tr_.mark(item, 2);
         q.advance();
     }
-    // the last CTA out returns the per-frame counters to zero for the next launch
-    if (q.finish())
+    publish_tile();
+    // the last group out returns the per-frame counters to zero for the next launch
+    if (q.finish(s_last))
         for (int i = tid; i < p.n_frames; i += kCT) p.tiles_done[i] = 0;
 }
 

@@ -415,11 +415,12 @@ __device__ __forceinline__ uint32_t sm_id() {
 }
 struct ItemTrace {
     unsigned long long* buf;  // [items][4] or null
+    int tid;                  // thread index inside the CTA / work group that processes the item
     __device__ __forceinline__ void mark(uint32_t item, int slot) const {
-        if (buf && threadIdx.x == 0) buf[(size_t)item * 4 + slot] = global_ns();
+        if (buf && tid == 0) buf[(size_t)item * 4 + slot] = global_ns();
     }
     __device__ __forceinline__ void kind(uint32_t item, uint32_t k) const {
-        if (buf && threadIdx.x == 0) buf[(size_t)item * 4 + 3] = (unsigned long long)k | ((unsigned long long)sm_id() << 8);
+        if (buf && tid == 0) buf[(size_t)item * 4 + 3] = (unsigned long long)k | ((unsigned long long)sm_id() << 8);
     }
 };
 
@@ -460,6 +461,10 @@ struct TicketQueue {
     // Call once, by all threads, when the CTA has no more work.  Returns true (to every thread) in the last CTA.
     __device__ __forceinline__ bool finish() {
         __shared__ int s_last;
+        return finish(&s_last);
+    }
+    // `flag`: one shared int (kernels that own all of their shared memory pass a slot of their dynamic block)
+    __device__ __forceinline__ bool finish(int* flag) {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -468,10 +473,10 @@ struct TicketQueue {
                 counter[0] = 0;
                 counter[2] = 0;
             }
-            s_last = last;
+            *flag = last;
         }
         __syncthreads();
-        return s_last != 0;
+        return *flag != 0;
     }
 };
 

@@ -75,6 +75,7 @@ struct Workspace {
     int frames_cap = 0;
     // cached CLAHE geometry
     int gw = 0, gh = 0, gtx = 0, gty = 0, nxc = 0, nyc = 0;
+    std::vector<int4> h_cells;   // host copy of the cell tables (x cells, then y cells)
 };
 
 // Small pool of host threads for the chroma plane of host-buffer calls.  In passthrough mode the chroma bytes never
@@ -446,6 +447,10 @@ void axis_cells(int n, float inv, int ntiles, int max_len, int align, std::vecto
     flush(start, n, cur);
 }
 
+#ifndef NV12EQ_CLAHE_UV_CHUNK
+#define NV12EQ_CLAHE_UV_CHUNK (128 << 10)
+#endif
+constexpr unsigned long long kUvChunk = NV12EQ_CLAHE_UV_CHUNK;   // chroma bytes per uv item (512 KB items measured 7 % slower at 1080p, equal at 4K)
 int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d_out, int n, size_t pitch, int w, int h,
                  int stride, double clip, int tx, int ty, int uv_mode, cudaStream_t st) {
     if (n == 0) return NV12EQ_OK;
@@ -471,6 +476,8 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
                                 cudaMemcpyHostToDevice, st));
         ws.gw = w; ws.gh = h; ws.gtx = tx; ws.gty = ty;
         ws.nxc = (int)xc.size(); ws.nyc = (int)yc.size();
+        ws.h_cells = xc;
+        ws.h_cells.insert(ws.h_cells.end(), yc.begin(), yc.end());
     }
 
     ClaheParams p{};
@@ -482,11 +489,16 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     p.nxc = ws.nxc; p.nyc = ws.nyc;
     p.xcells = reinterpret_cast<const int4*>(ws.cells.p);
     p.ycells = p.xcells + ws.nxc;
+    p.cells_in_params = (ws.nxc <= kParamCells && ws.nyc <= kParamCells);
+    if (p.cells_in_params) {
+        std::copy(ws.h_cells.begin(), ws.h_cells.begin() + ws.nxc, p.xc_small);
+        std::copy(ws.h_cells.begin() + ws.nxc, ws.h_cells.end(), p.yc_small);
+    }
     const bool uv_work = (uv_mode == UV_GRAY128) || (uv_mode == UV_COPY && d_in != d_out);
     p.uv_bytes = (unsigned long long)w * (h / 2);
     int U = 0;
     if (uv_work && h / 2 > 0) {
-        U = (int)std::max<unsigned long long>(1, (p.uv_bytes + 131071) / 131072);
+        U = (int)std::max<unsigned long long>(1, (p.uv_bytes + kUvChunk - 1) / kUvChunk);
         if (!p.flat) U = std::min(U, h / 2);
         p.uv_chunk = std::max<unsigned long long>(4096, (((p.uv_bytes + U - 1) / U) + 4095ull) & ~4095ull);
         p.uv_rows_chunk = (h / 2 + U - 1) / U;
@@ -503,11 +515,11 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     // 4K frames with cool-downs between runs (tools/sweep.py --ctas 4,3,4,3 --cooldown 4): 8x8 grid (130 K-pixel tiles) 7.22 vs
     // 7.35 us per frame, 6x6 (230 K) 7.05 vs 7.04, 4x4 (518 K) 7.56 vs 7.48 -- the extra CTA wins until the tiles are so
     // large that the per-item phases no longer matter.
-    const int auto_ctas = ((long long)g.tw * g.th >= 262144 && kClaheCtas > 2) ? kClaheCtas - 1 : kClaheCtas;
+    const int auto_ctas = kClaheCtas;
     const int per_sm = ctx->tune_ctas > 0 ? std::min(ctx->tune_ctas, kClaheCtas) : auto_ctas;
     {
         // same reasoning as for equalizeHist; tile items run ~1.5x longer than the average item
-        const long long grid_ctas = (long long)ctx->sm_count * per_sm;
+        const long long grid_ctas = (long long)ctx->sm_count * per_sm * kGroups;   // work groups drawing tickets
         long long lag = (3 * grid_ctas / 2 + per_slot - 1) / per_slot + 1;
         const long long cap = std::max<long long>(1, (48ll << 20) / std::max<long long>(1, (long long)w * h));
         lag = std::min(lag, cap);
@@ -526,10 +538,10 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
         if (rc) return rc;
         p.trace = reinterpret_cast<unsigned long long*>(trace_buf.p);
     }
-    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * per_sm, items));
-    if (per_sm <= 1) clahe_kernel<1><<<grid, kCT, kClaheSmemBytes, st>>>(p);
-    else if (per_sm < kClaheCtas) clahe_kernel<kClaheCtas - 1><<<grid, kCT, kClaheSmemBytes, st>>>(p);
-    else clahe_kernel<kClaheCtas><<<grid, kCT, kClaheSmemBytes, st>>>(p);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->sm_count * per_sm, (items + kGroups - 1) / kGroups));
+    if (per_sm <= 1) clahe_kernel<1><<<grid, kBlockThreads, kClaheSmemBytes, st>>>(p);
+    else if (per_sm < kClaheCtas) clahe_kernel<kClaheCtas - 1><<<grid, kBlockThreads, kClaheSmemBytes, st>>>(p);
+    else clahe_kernel<kClaheCtas><<<grid, kBlockThreads, kClaheSmemBytes, st>>>(p);
     ctx->ctr.kernel_launches++;
     CK(ctx, cudaGetLastError());
     if (trace_path) {

@@ -1,0 +1,234 @@
+// Developer tool: the CLAHE cell-loop body (gather + unfused fp32 blend + pack) in isolation, in several formulations that
+// all compute OpenCV's arithmetic bit for bit; prints cycles per 32 pixels per SM sub-partition at 8 warps per sub-partition
+// (the occupancy of clahe_kernel) and a checksum per variant (all checksums must agree).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build_tmp/blend_bench tools/blend_bench.cu && build_tmp/blend_bench
+// Pixels come from shared memory and go back to shared memory, so only the SM's issue slots and pipes are measured.
+#include <cstdio>
+#include <cstdint>
+#include <cmath>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#define SBASE "1024"
+extern __shared__ __align__(256) uint32_t smem_rows[];
+constexpr int kThreads = 1024;
+constexpr int kRowBytes = 256;
+constexpr int kTableBytes = 256 * kRowBytes;      // 64 KB, rows of 256 bytes (the variant uses the first 128 bytes)
+constexpr int kRingOff = kTableBytes;             // [4 slots][kThreads] 16 bytes
+constexpr int kOutOff = kRingOff + 4 * kThreads * 16;
+constexpr int kYwOff = kOutOff + kThreads * 16;   // [64] 8 bytes
+constexpr int kSmem = kYwOff + 64 * 8;
+
+__device__ __forceinline__ uint64_t pack_f2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ uint64_t pack_u2(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void unpack_u2(uint64_t v, uint32_t& a, uint32_t& b) { asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul_f2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t add_f2_nofuse(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint2 lds64_rel(uint32_t off) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+" SBASE "];" : "=r"(v.x), "=r"(v.y) : "r"(off)); return v; }
+__device__ __forceinline__ uint32_t lds32_rel(uint32_t off) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1+" SBASE "];" : "=r"(v) : "r"(off)); return v; }
+__device__ __forceinline__ uint64_t lds_b64_rel(uint32_t off) { uint64_t v; asm volatile("ld.shared.b64 %0, [%1+" SBASE "];" : "=l"(v) : "r"(off)); return v; }
+__device__ __forceinline__ uint4 lds128_rel(uint32_t off) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+" SBASE "];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(off)); return v; }
+__device__ __forceinline__ void sts128_rel(uint32_t off, uint4 v) { asm volatile("st.shared.v4.u32 [%0+" SBASE "], {%1, %2, %3, %4};" ::"r"(off), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+template <int K> __device__ __forceinline__ uint32_t row_off(uint32_t w, uint32_t lane_off) { return __byte_perm(w, lane_off, 0x5504u | (K << 4)); }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r; }
+
+// Variants
+//  0: 8-byte entries {bf16 L11 | bf16 L21 << 16, bf16 L12 | bf16 L22 << 16}, unpack by shift / mask as the compiler likes (round 1)
+//  1: same entries, unpack with explicit PRMTs (alu pipe only)
+//  2: 4-byte entries {L11, L21, L12, L22} bytes, 32 replicas; unpack with PRMT to SUBNORMAL floats v * 2^-149; x weights carry
+//     2^100 and y weights 2^49 (exact power-of-two scalings: every rounding happens on the same significand)
+//  3: 8-byte entries {L11 | L21 << 24, L12 | L22 << 24}, unpack with one IMAD.WIDE each (lanes v * 2^-141 and v * 2^-149)
+//  4: 16-byte fp32 entries (LDS.128, 8 replicas), no unpack
+//  5: variant 1 with scalar fp32 arithmetic instead of packed
+//  6: variant 2 with the x weights pinned in registers (no re-derivation of 1 - xa)
+//  7: variant 1 with the x weights pinned
+template <int V>
+struct Blend {
+    static constexpr bool kByteTable = (V == 2 || V == 6);
+    static constexpr float kXScale = (V == 2 || V == 6 || V == 3) ? 1.2676506002282294e30f /* 2^100 */ : 1.0f;
+    __device__ static __forceinline__ uint32_t lane_off(int lane) { return kByteTable ? lane * 4 : (V == 4 ? (lane & 7) * 16 : (lane & 15) * 8); }
+    // table fill: row v
+    __device__ static void fill_row(uint8_t* row, uint32_t l11, uint32_t l12, uint32_t l21, uint32_t l22) {
+        if (kByteTable) {
+            for (int j = 0; j < 32; ++j) reinterpret_cast<uint32_t*>(row)[j] = l11 | (l21 << 8) | (l12 << 16) | (l22 << 24);
+        } else if (V == 3) {
+            for (int j = 0; j < 16; ++j) reinterpret_cast<uint2*>(row)[j] = make_uint2(l11 | (l21 << 24), l12 | (l22 << 24));
+        } else if (V == 8 || V == 10) {
+            uint2 e;
+            e.x = __half_as_ushort(__float2half((float)l11)) | ((uint32_t)__half_as_ushort(__float2half((float)l21)) << 16);
+            e.y = __half_as_ushort(__float2half((float)l12)) | ((uint32_t)__half_as_ushort(__float2half((float)l22)) << 16);
+            if (V == 10) e.y = (__float_as_uint((float)l12) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
+            for (int j = 0; j < 16; ++j) reinterpret_cast<uint2*>(row)[j] = e;
+        } else if (V == 4) {
+            for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(row)[j] = make_float4((float)l11, (float)l21, (float)l12, (float)l22);
+        } else {
+            uint2 e;
+            e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l21) & 0xffff0000u);
+            e.y = (__float_as_uint((float)l12) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
+            for (int j = 0; j < 16; ++j) reinterpret_cast<uint2*>(row)[j] = e;
+        }
+    }
+    // y weights as stored in shared memory
+    __device__ static float2 yw(float ya1, float ya) {
+        if (V == 2 || V == 6) return make_float2(ya1 * 5.62949953421312e14f, ya * 5.62949953421312e14f);        // 2^49
+        if (V == 3) return make_float2(ya1 * 2199023255552.0f /* 2^41 */, ya * 5.62949953421312e14f /* 2^49 */);
+        return make_float2(ya1, ya);
+    }
+    template <int K>
+    __device__ static __forceinline__ float px(uint32_t w, uint32_t lo, float xa, float xa1, uint64_t ywp, uint32_t mulreg) {
+        uint64_t A, B;
+        if (V == 0) {
+            const uint2 e = lds64_rel(row_off<K>(w, lo));
+            A = pack_f2(__uint_as_float(e.x << 16), __uint_as_float(e.x & 0xffff0000u));
+            B = pack_f2(__uint_as_float(e.y << 16), __uint_as_float(e.y & 0xffff0000u));
+        } else if (V == 1 || V == 5 || V == 7 || V == 9) {
+            const uint2 e = lds64_rel(V == 9 ? (lo & 8u) : row_off<K>(w, lo));
+            A = pack_u2(prmt(e.x, 0, 0x1044), prmt(e.x, 0, 0x3244));
+            B = pack_u2(prmt(e.y, 0, 0x1044), prmt(e.y, 0, 0x3244));
+        } else if (V == 8) {
+            const uint2 e = lds64_rel(row_off<K>(w, lo));
+            float a0, a1, b0, b1;
+            asm("{ .reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(a0), "=f"(a1) : "r"(e.x));
+            asm("{ .reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(b0), "=f"(b1) : "r"(e.y));
+            A = pack_f2(a0, a1); B = pack_f2(b0, b1);
+        } else if (V == 10) {   // half the unpack on the fma pipe (fp16 conversion), half on the alu pipe (PRMT of the other table word, bf16)
+            const uint2 e = lds64_rel(row_off<K>(w, lo));
+            float a0, a1;
+            asm("{ .reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(a0), "=f"(a1) : "r"(e.x));
+            A = pack_f2(a0, a1);
+            B = pack_u2(prmt(e.y, 0, 0x1044), prmt(e.y, 0, 0x3244));
+        } else if (kByteTable) {
+            const uint32_t e = lds32_rel(row_off<K>(w, lo));
+            A = pack_u2(prmt(e, 0, 0x4440), prmt(e, 0, 0x4441));
+            B = pack_u2(prmt(e, 0, 0x4442), prmt(e, 0, 0x4443));
+        } else if (V == 3) {
+            const uint2 e = lds64_rel(row_off<K>(w, lo));
+            asm("mul.wide.u32 %0, %1, %2;" : "=l"(A) : "r"(e.x), "r"(mulreg));
+            asm("mul.wide.u32 %0, %1, %2;" : "=l"(B) : "r"(e.y), "r"(mulreg));
+        } else {
+            const uint4 e = lds128_rel(row_off<K>(w, lo));
+            A = pack_u2(e.x, e.y);
+            B = pack_u2(e.z, e.w);
+        }
+        if (V == 5) {
+            float a0, a1, b0, b1, y0, y1;
+            unpack_f2(A, a0, a1); unpack_f2(B, b0, b1); unpack_f2(ywp, y0, y1);
+            const float top = __fadd_rn(__fmul_rn(a0, xa1), __fmul_rn(b0, xa));
+            const float bot = __fadd_rn(__fmul_rn(a1, xa1), __fmul_rn(b1, xa));
+            return __fadd_rn(__fmul_rn(top, y0), __fmul_rn(bot, y1));
+        }
+        const uint64_t S = add_f2_nofuse(mul_f2(A, pack_f2(xa1, xa1)), mul_f2(B, pack_f2(xa, xa)));
+        float r0, r1;
+        unpack_f2(mul_f2(S, ywp), r0, r1);
+        return __fadd_rn(r0, r1);
+    }
+};
+__device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+__device__ __forceinline__ void round_pair(float a, float b, uint32_t& oa, uint32_t& ob) {
+    unpack_u2(add_f2(pack_f2(a, b), pack_f2(12582912.0f, 12582912.0f)), oa, ob);
+}
+
+template <int V>
+__global__ void __launch_bounds__(kThreads, 1) blend_kernel(unsigned long long* out, int iters, float inv_tw, float inv_th, uint32_t mulreg) {
+    uint8_t* const rows = reinterpret_cast<uint8_t*>(smem_rows);
+    const int tid = threadIdx.x, lane = tid & 31;
+    using B = Blend<V>;
+    if ((uint32_t)__cvta_generic_to_shared(rows) != 1024u) { if (tid == 0) out[2] = 99; return; }
+    // tables and pixels
+    for (int v = tid; v < 256; v += kThreads)
+        B::fill_row(rows + v * kRowBytes, (v * 7 + 3) & 255, (v * 13 + 5) & 255, (255 - v), (v * 29 + 11) & 255);
+    for (int i = tid; i < 4 * kThreads * 4; i += kThreads) {
+        uint32_t h = i * 2654435761u; h ^= h >> 13; h *= 0x9e3779b1u; h ^= h >> 16;
+        reinterpret_cast<uint32_t*>(rows + kRingOff)[i] = h;
+    }
+    for (int i = tid; i < 64; i += kThreads) {
+        const float f = (i + 100) * inv_th - 0.5f;
+        const float ya = f - floorf(f), ya1 = 1.0f - ya;
+        reinterpret_cast<float2*>(rows + kYwOff)[i] = B::yw(ya1, ya);
+    }
+    __syncthreads();
+    float xa[16], xa1[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float f = __fsub_rn(__fmul_rn((float)(tid * 16 + k + 240), inv_tw), 0.5f);
+        const float a = __fsub_rn(f, floorf(f));
+        xa[k] = a * B::kXScale;
+        xa1[k] = __fsub_rn(1.0f, a) * B::kXScale;
+        if (V == 6 || V == 7) asm volatile("" : "+f"(xa1[k]));
+    }
+    const uint32_t lo = B::lane_off(lane);
+    const uint32_t ring0 = kRingOff + tid * 16, out0 = kOutOff + tid * 16;
+    uint32_t yw_off = kYwOff;
+    uint32_t sum = 0;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; it += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 p = lds128_rel(ring0 + j * kThreads * 16);
+            const uint64_t ywp = lds_b64_rel(yw_off + j * 8);
+            const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float f0 = B::template px<0>(w[q], lo, xa[4 * q + 0], xa1[4 * q + 0], ywp, mulreg);
+                const float f1 = B::template px<1>(w[q], lo, xa[4 * q + 1], xa1[4 * q + 1], ywp, mulreg);
+                const float f2 = B::template px<2>(w[q], lo, xa[4 * q + 2], xa1[4 * q + 2], ywp, mulreg);
+                const float f3 = B::template px<3>(w[q], lo, xa[4 * q + 3], xa1[4 * q + 3], ywp, mulreg);
+                uint32_t a, b, c, d;
+                round_pair(f0, f1, a, b);
+                round_pair(f2, f3, c, d);
+                o[q] = pack_low_bytes(a, b, c, d);
+            }
+            sts128_rel(out0, make_uint4(o[0], o[1], o[2], o[3]));
+            sum += o[0] ^ o[1] ^ o[2] ^ o[3];
+        }
+        yw_off = kYwOff + ((it * 8) & 255);
+    }
+    const long long t1 = clock64();
+    atomicAdd(reinterpret_cast<unsigned int*>(out + 1), sum);
+    if (tid == 0 && blockIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+}
+
+template <int V>
+void run(const char* name, unsigned long long* d_out, int threads = kThreads) {
+    const int iters = 4096;
+    cudaFuncSetAttribute(blend_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    unsigned long long h[3] = {0, 0, 0};
+    for (int k = 0; k < 2; ++k) {
+        cudaMemset(d_out, 0, 24);
+        blend_kernel<V><<<148, threads, kSmem>>>(d_out, iters, 1.0f / 480.0f, 1.0f / 270.0f, 256u);
+    }
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, d_out, 24, cudaMemcpyDeviceToHost);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, blend_kernel<V>);
+    // 8 warps per sub-partition, 16 pixels per lane and iteration
+    printf("%-64s %6.2f cycles per 32 pixels per sub-partition, %3d regs, checksum %08x %s %s\n", name, (double)h[0] / ((double)iters * 16.0 * (threads / 128)),
+           fa.numRegs, (unsigned)h[1], h[2] ? "SMEM BASE MISMATCH" : "", cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+    unsigned long long* d_out;
+    cudaMalloc(&d_out, 64);
+    run<0>("0: bf16 pairs, shift/mask unpack (round 1)", d_out);
+    run<1>("1: bf16 pairs, PRMT unpack", d_out);
+    run<7>("7: bf16 pairs, PRMT unpack, x weights pinned", d_out);
+    run<2>("2: byte entries (LDS.32), PRMT to subnormals, scaled weights", d_out);
+    run<6>("6: byte entries, x weights pinned", d_out);
+    run<3>("3: {L | L << 24} words, IMAD.WIDE unpack", d_out);
+    run<4>("4: fp32 entries (LDS.128), no unpack", d_out);
+    run<5>("5: bf16 pairs, PRMT unpack, scalar fp32", d_out);
+    run<8>("8: fp16 pairs, cvt.f32.f16 unpack (fma pipe)", d_out);
+    run<10>("10: half fp16 cvt, half PRMT", d_out);
+    run<9>("9: variant 1, every lane gathers row 0 (checksum differs)", d_out);
+    run<1>("1 at 6 warps per sub-partition", d_out, 768);
+    run<1>("1 at 4 warps per sub-partition", d_out, 512);
+    run<1>("1 at 2 warps per sub-partition", d_out, 256);
+    run<7>("7 at 4 warps per sub-partition", d_out, 512);
+    return 0;
+}
