@@ -80,7 +80,11 @@ constexpr int kIterDepth = NV12EQ_CLAHE_DEPTH;  // row iterations in flight per 
 #ifndef NV12EQ_CLAHE_G16
 #define NV12EQ_CLAHE_G16 1
 #endif
-constexpr bool kUseG16 = NV12EQ_CLAHE_G16 != 0;   // 16 pixels per thread-row where alignment allows (32 registers of x weights); else 8 pixels x 2 rows
+constexpr bool kUseG16 = NV12EQ_CLAHE_G16 != 0;
+#ifndef NV12EQ_CLAHE_ROWS16
+#define NV12EQ_CLAHE_ROWS16 1
+#endif
+constexpr int kRows16 = NV12EQ_CLAHE_ROWS16;      // rows per loop iteration of the 16-pixel path (1: four iterations in flight, 2: two)   // 16 pixels per thread-row where alignment allows (32 registers of x weights); else 8 pixels x 2 rows
 // shared memory map (byte offsets from the start of nv12eq_smem_rows); per-group areas are indexed by the group
 constexpr int kRingOff = kRowTableBytes;                                   // [kGroups][kCT * kRingBytesPerThread]
 constexpr int kRingGroupBytes = kCT * kRingBytesPerThread;
@@ -383,9 +387,64 @@ __device__ __forceinline__ uint64_t add_f2_nofuse(uint64_t a, uint64_t b) {
 }
 // res of one pixel: 0 <= res < 255.5 (convex-ish combination of values in [0,255]), so adding 1.5*2^23 afterwards
 // performs cvRound's round-half-to-even and leaves the integer in the low mantissa byte; saturate_cast is the identity.
-__device__ __forceinline__ float clahe_blend_res(uint2 e, float xa, float xa1, uint64_t yw) {
-    const uint64_t A = pack_f2(__uint_as_float(e.x << 16), __uint_as_float(e.x & 0xffff0000u));  // (L11, L21)
-    const uint64_t B = pack_f2(__uint_as_float(e.y << 16), __uint_as_float(e.y & 0xffff0000u));  // (L12, L22)
+#ifndef NV12EQ_CLAHE_UNPACK_PRMT
+#define NV12EQ_CLAHE_UNPACK_PRMT 1
+#endif
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack_u2(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub_f2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// bf16 pair -> packed fp32 pair.  With PRMT both halves are alu-pipe operations; left to the compiler, the low half becomes
+// an IMAD.U32 on the fma pipe, which the blend's FMUL2 / FADD2 already load the most (tools/blend_bench.cu, pipe_rates.cu:
+// f32x2 operations and all alu-pipe operations take two cycles per warp on a sub-partition, scalar fp32 one).
+__device__ __forceinline__ uint64_t bf16x2_to_f2(uint32_t e) {
+#if NV12EQ_CLAHE_UNPACK_PRMT
+    return pack_u2(prmt_b32(e, 0u, 0x1044u), prmt_b32(e, 0u, 0x3244u));
+#else
+    return pack_f2(__uint_as_float(e << 16), __uint_as_float(e & 0xffff0000u));
+#endif
+}
+// Table entry of one pixel value.  Two formats:
+//   bf16 pairs (8 bytes, 16 replicas per row): {bf16 L11 | bf16 L21 << 16, bf16 L12 | bf16 L22 << 16}
+//   bytes      (4 bytes, 32 replicas per row): L11 | L21 << 8 | L12 << 16 | L22 << 24.  A byte moved to the low end of a zero
+//              word IS the fp32 subnormal L * 2^-149; the x weights carry 2^100 and the y weights 2^49, so every product and
+//              sum is the reference's value times an exact power of two (same significand, same rounding; all intermediate
+//              values are normal or zero: L * xa * 2^-49 >= 2^-75) and the final sum comes out unscaled.  One shared
+//              wavefront per warp-wide gather instead of two (tools/blend_bench.cu checks both against each other).
+#ifndef NV12EQ_CLAHE_BYTE_TABLE
+#define NV12EQ_CLAHE_BYTE_TABLE 1
+#endif
+constexpr bool kByteTable = NV12EQ_CLAHE_BYTE_TABLE != 0;
+constexpr float kXScale = kByteTable ? 1.2676506002282294e30f /* 2^100 */ : 1.0f;
+constexpr float kYScale = kByteTable ? 5.62949953421312e14f /* 2^49 */ : 1.0f;
+struct TableEntry {
+    uint32_t x, y;   // bytes format: x only
+};
+__device__ __forceinline__ TableEntry lds_entry_rel(uint32_t off) {
+    TableEntry e;
+    if (kByteTable) {
+        asm volatile("ld.shared.u32 %0, [%1+" NV12EQ_SBASE "];" : "=r"(e.x) : "r"(off));
+        e.y = 0;
+    } else {
+        const uint2 v = lds64_rel(off);
+        e.x = v.x; e.y = v.y;
+    }
+    return e;
+}
+__device__ __forceinline__ float clahe_blend_res(TableEntry e, float xa, float xa1, uint64_t yw) {
+    const uint64_t A = kByteTable ? pack_u2(prmt_b32(e.x, 0u, 0x4440u), prmt_b32(e.x, 0u, 0x4441u)) : bf16x2_to_f2(e.x);  // (L11, L21)
+    const uint64_t B = kByteTable ? pack_u2(prmt_b32(e.x, 0u, 0x4442u), prmt_b32(e.x, 0u, 0x4443u)) : bf16x2_to_f2(e.y);  // (L12, L22)
     const uint64_t S = add_f2_nofuse(mul_f2(A, pack_f2(xa1, xa1)), mul_f2(B, pack_f2(xa, xa)));   // (top, bot)
     float r0, r1;
     unpack_f2(mul_f2(S, yw), r0, r1);  // (top*ya1, bot*ya)
@@ -393,7 +452,7 @@ __device__ __forceinline__ float clahe_blend_res(uint2 e, float xa, float xa1, u
 }
 template <int K>
 __device__ __forceinline__ float clahe_blend_px(uint32_t w, uint32_t lane8, float xa, float xa1, uint64_t yw) {
-    return clahe_blend_res(lds64_rel(row_off<K>(w, lane8)), xa, xa1, yw);
+    return clahe_blend_res(lds_entry_rel(row_off<K>(w, lane8)), xa, xa1, yw);
 }
 __device__ __forceinline__ void round_pair(float a, float b, uint32_t& oa, uint32_t& ob) {
     unpack_u2(add_f2(pack_f2(a, b), pack_f2(12582912.0f, 12582912.0f)), oa, ob);
@@ -402,21 +461,35 @@ __device__ __forceinline__ void round_pair(float a, float b, uint32_t& oa, uint3
 __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
-// eight horizontally adjacent pixels (two packed words) -> two packed output words
-__device__ __forceinline__ uint2 clahe_blend_8(uint2 px, uint32_t lane8, const float* xa, const float* xa1, uint64_t yw) {
-    float f[8];
-    f[0] = clahe_blend_px<0>(px.x, lane8, xa[0], xa1[0], yw);
-    f[1] = clahe_blend_px<1>(px.x, lane8, xa[1], xa1[1], yw);
-    f[2] = clahe_blend_px<2>(px.x, lane8, xa[2], xa1[2], yw);
-    f[3] = clahe_blend_px<3>(px.x, lane8, xa[3], xa1[3], yw);
-    f[4] = clahe_blend_px<0>(px.y, lane8, xa[4], xa1[4], yw);
-    f[5] = clahe_blend_px<1>(px.y, lane8, xa[5], xa1[5], yw);
-    f[6] = clahe_blend_px<2>(px.y, lane8, xa[6], xa1[6], yw);
-    f[7] = clahe_blend_px<3>(px.y, lane8, xa[7], xa1[7], yw);
-    uint32_t o[8];
+// Pixels 2P and 2P+1 of word q of R rows: the x weights of a pixel pair travel as one packed register pair, and the pair
+// (1 - xa) is ONE packed subtraction shared by the R rows -- the compiler otherwise re-derives 1 - xa per pixel and row (a
+// 64-register kernel cannot hold 32 x weights) with scalar FADDs.
+template <int P, int R>
+__device__ __forceinline__ void clahe_blend_pair(const uint32_t (&w)[R], uint32_t lane8, uint64_t xap, const uint64_t (&yw)[R], uint32_t (&o)[R][4]) {
+    const uint64_t xa1p = sub_f2(pack_f2(kXScale, kXScale), xap);   // (1 - xa) * kXScale, exactly
+    float xa0, xa1, xb0, xb1;
+    unpack_f2(xap, xa0, xa1);
+    unpack_f2(xa1p, xb0, xb1);
 #pragma unroll
-    for (int k = 0; k < 8; k += 2) round_pair(f[k], f[k + 1], o[k], o[k + 1]);
-    return make_uint2(pack_low_bytes(o[0], o[1], o[2], o[3]), pack_low_bytes(o[4], o[5], o[6], o[7]));
+    for (int r = 0; r < R; ++r) {
+        const float f0 = clahe_blend_px<2 * P>(w[r], lane8, xa0, xb0, yw[r]);
+        const float f1 = clahe_blend_px<2 * P + 1>(w[r], lane8, xa1, xb1, yw[r]);
+        round_pair(f0, f1, o[r][2 * P], o[r][2 * P + 1]);
+    }
+}
+// NW packed words (4 pixels each) of R rows that share their x weights xw[2 * NW] (pixel pairs)
+template <int NW, int R>
+__device__ __forceinline__ void clahe_blend_rows(const uint32_t (&px)[R][NW], uint32_t lane8, const uint64_t* xw, const uint64_t (&yw)[R], uint32_t (&out)[R][NW]) {
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+        uint32_t w[R], o[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r) w[r] = px[r][q];
+        clahe_blend_pair<0, R>(w, lane8, xw[2 * q], yw, o);
+        clahe_blend_pair<1, R>(w, lane8, xw[2 * q + 1], yw, o);
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r][q] = pack_low_bytes(o[r][0], o[r][1], o[r][2], o[r][3]);
+    }
 }
 
 __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float& a1) {
@@ -427,17 +500,16 @@ __device__ __forceinline__ void axis_weight(int pos, float inv, float& a, float&
 }
 
 // The rows of one thread inside a cell: G (8 or 16) horizontally adjacent pixels per row, rows tr, tr + rpp, ...; R of
-// them per loop iteration (the x weights are shared by all rows, so R = 2 halves the per-iteration overhead per pixel
-// without more weight registers -- what the 8-pixel path of small cells needs).  Thread-private ring of D * R G-byte slots
-// in the spare half of the thread's own table row, filled with cp.async: the rows of D - 1 iterations ahead are in flight
-// without holding registers, and since a thread only ever reads its own slots no barrier is involved.  The loop is unrolled
-// by D, so every ring slot is a compile-time offset.  Thread 0 (tr == 0, the most rows) draws the next ticket at the start of
-// the last round, which hides the atomic's round trip.
-template <int G, int R>
+// them per loop iteration (the x weights are shared by all rows, so R = 2 halves the per-iteration overhead and the
+// re-derivation of 1 - xa per pixel).  Thread-private ring of D * R G-byte slots, filled with cp.async: the rows of D - 1
+// iterations ahead are in flight without holding registers, and since a thread only ever reads its own slots no barrier is
+// involved.  The loop is unrolled by D, so every ring slot is a compile-time offset.  Thread 0 (tr == 0, the most rows) draws
+// the next ticket at the start of the last round, which hides the atomic's round trip.
+template <int G, int R, int D>
 struct CellRows {
-    static constexpr int D = kIterDepth;
     static_assert(D * R * G <= kRingBytesPerThread, "ring must fit the thread's slots");
-    float xa[G], xa1[G];
+    static constexpr int NW = G / 4;   // packed pixel words per row
+    uint64_t xw[G / 2];                // x weights (xa) of pixel pairs
     const uint8_t* spn;
     uint8_t* dp;
     size_t rstep;
@@ -459,11 +531,11 @@ struct CellRows {
                                           uint32_t yw_off_, uint32_t yw_step_) {
         dp = dp_; rstep = rstep_; nrows = nrows_; ring0 = ring_base(tid, group); yw_off = yw_off_; yw_step = yw_step_;
 #pragma unroll
-        for (int k = 0; k < G; ++k) {
-            axis_weight(xg + k, inv_tw, xa[k], xa1[k]);
-#ifdef NV12EQ_CLAHE_PIN
-            asm volatile("" : "+f"(xa1[k]));   // keep 1 - xa in its register: stops the compiler re-deriving it per pixel
-#endif
+        for (int k = 0; k < G; k += 2) {
+            float a0, a1, b0, b1;
+            axis_weight(xg + k, inv_tw, a0, b0);
+            axis_weight(xg + k + 1, inv_tw, a1, b1);
+            xw[k / 2] = pack_f2(a0 * kXScale, a1 * kXScale);
         }
 #pragma unroll
         for (int j = 0; j < D - 1; ++j) {
@@ -487,20 +559,27 @@ struct CellRows {
                         if (i + (D - 1) * R + r < nrows) issue(((j + D - 1) % D) * R + r, spn + (size_t)r * rstep);
                     cp_async_commit();
                     cp_async_wait<D - 1>();
+                    // a row past the end of the cell (odd row count, R = 2) is blended from stale ring bytes and not stored
+                    uint32_t px[R][NW], out[R][NW];
+                    uint64_t yw[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        yw[r] = (r == 0 || i + r < nrows) ? lds_b64_rel(yw_off + (uint32_t)r * yw_step) : 0ull;   // (the weight table ends with the cell)
+                        if (G == 16) {
+                            const int4 v = lds128_rel(ring0 + (uint32_t)(j * R + r) * kSlotStride);
+                            px[r][0] = (uint32_t)v.x; px[r][1] = (uint32_t)v.y; px[r][NW - 2] = (uint32_t)v.z; px[r][NW - 1] = (uint32_t)v.w;
+                        } else {
+                            const uint2 v = lds64_rel(ring0 + (uint32_t)(j * R + r) * kSlotStride);
+                            px[r][0] = v.x; px[r][NW - 1] = v.y;
+                        }
+                    }
+                    clahe_blend_rows<NW, R>(px, lane8, xw, yw, out);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         if (r == 0 || i + r < nrows) {
-                            const uint64_t yw = lds_b64_rel(yw_off + (uint32_t)r * yw_step);
                             uint8_t* d = dp + (size_t)r * rstep;
-                            if (G == 16) {
-                                const int4 px = lds128_rel(ring0 + (uint32_t)(j * R + r) * kSlotStride);
-                                const uint2 o0 = clahe_blend_8(make_uint2((uint32_t)px.x, (uint32_t)px.y), lane8, xa, xa1, yw);
-                                const uint2 o1 = clahe_blend_8(make_uint2((uint32_t)px.z, (uint32_t)px.w), lane8, xa + 8 * (G / 16), xa1 + 8 * (G / 16), yw);
-                                __stcs(reinterpret_cast<uint4*>(d), make_uint4(o0.x, o0.y, o1.x, o1.y));
-                            } else {
-                                const uint2 px = lds64_rel(ring0 + (uint32_t)(j * R + r) * kSlotStride);
-                                __stcs(reinterpret_cast<uint2*>(d), clahe_blend_8(px, lane8, xa, xa1, yw));
-                            }
+                            if (G == 16) __stcs(reinterpret_cast<uint4*>(d), make_uint4(out[r][0], out[r][1], out[r][NW - 2], out[r][NW - 1]));
+                            else __stcs(reinterpret_cast<uint2*>(d), make_uint2(out[r][0], out[r][NW - 1]));
                         }
                     }
                     spn += (size_t)R * rstep; dp += (size_t)R * rstep; yw_off += (uint32_t)R * yw_step;
@@ -532,7 +611,8 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const Cl
     const int per_slot = T + I + U;
     const uint32_t total_items = (uint32_t)(p.n_frames + p.lag) * (uint32_t)per_slot;
     const uint32_t lane4 = (uint32_t)(group * kHalfBytes + lane * 4);                        // hist column of this lane
-    const uint32_t lane8 = (uint32_t)(group * kHalfBytes + (lane & (kCellReps - 1)) * 8);    // cell table replica of this lane
+    const uint32_t lane8 = kByteTable ? (uint32_t)(group * kHalfBytes + lane * 4)                               // cell table replica of this lane
+                                      : (uint32_t)(group * kHalfBytes + (lane & (kCellReps - 1)) * 8);
     const uint32_t yw_base = (uint32_t)(kYwOff + group * kMaxCellRows * 8);
 
     GroupTickets q{p.ticket, s_ticket, tid, bar, p, total_items, (uint32_t)per_slot, T, I, 0u, 0u, 0u, false};
@@ -642,7 +722,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const Cl
                     for (int i = tid; i < ch; i += kCT) {
                         float ya, ya1;
                         axis_weight(yc.x + i, p.inv_th, ya, ya1);
-                        s_yw[i] = make_float2(ya1, ya);
+                        s_yw[i] = make_float2(ya1 * kYScale, ya * kYScale);
                     }
                     if (!q.current_ready()) {   // look-ahead did not see the tiles complete: poll (rare in steady state)
                         if (tid == 0) {
@@ -673,8 +753,13 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const Cl
                         const uint32_t l21 = __ldcg(L + (size_t)(yc.w * p.tx + xc.z) * 256 + v);
                         const uint32_t l22 = __ldcg(L + (size_t)(yc.w * p.tx + xc.w) * 256 + v);
                         uint4 e;
-                        e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l21) & 0xffff0000u);
-                        e.y = (__float_as_uint((float)l12) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
+                        if (kByteTable) {
+                            e.x = l11 | (l21 << 8) | (l12 << 16) | (l22 << 24);
+                            e.y = e.x;
+                        } else {
+                            e.x = (__float_as_uint((float)l11) >> 16) | (__float_as_uint((float)l21) & 0xffff0000u);
+                            e.y = (__float_as_uint((float)l12) >> 16) | (__float_as_uint((float)l22) & 0xffff0000u);
+                        }
                         e.z = e.x; e.w = e.y;
                         uint4* row = reinterpret_cast<uint4*>(half + v * kRowBytes);
 #pragma unroll
@@ -685,12 +770,12 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const Cl
                 };
                 bool ok;
                 if (fast16 && kUseG16) {
-                    CellRows<16, 1> cr;
+                    CellRows<16, kRows16, kRingBytesPerThread / (16 * kRows16)> cr;
                     cr.start(sp, dp, rstep, nrows, xg, p.inv_tw, tid, group, yw_off, yw_step);
                     ok = wait_and_build_table();
                     if (ok) cr.run(q, lane8);
                 } else {
-                    CellRows<8, 2> cr;
+                    CellRows<8, 2, kRingBytesPerThread / 16> cr;
                     cr.start(sp, dp, rstep, nrows, xg, p.inv_tw, tid, group, yw_off, yw_step);
                     ok = wait_and_build_table();
                     if (ok) cr.run(q, lane8);
@@ -706,7 +791,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const Cl
                         float xa, xa1;
                         axis_weight(x, p.inv_tw, xa, xa1);
                         const uint32_t v = src[(size_t)yy * p.stride + x];
-                        const float res = clahe_blend_res(lds64_rel((v << kRowShift) + lane8), xa, xa1, lds_b64_rel(yw_base + (uint32_t)ry * 8u));
+                        const float res = clahe_blend_res(lds_entry_rel((v << kRowShift) + lane8), xa * kXScale, xa1 * kXScale, lds_b64_rel(yw_base + (uint32_t)ry * 8u));
                         dst[(size_t)yy * p.stride + x] = (uint8_t)__float_as_uint(__fadd_rn(res, 12582912.0f));
                     }
                 }
