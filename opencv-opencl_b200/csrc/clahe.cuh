@@ -27,6 +27,7 @@
 // Roofline: HBM, 3*W*H algorithmic bytes per frame (tile LUTs are 16 KB per frame).  Secondary limiters: shared
 // atomics (tile items) and instruction issue (cell items: ~15 instructions per pixel).
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include "common.cuh"
 
 // Dynamic shared memory of clahe_kernel.  The kernel owns ALL of its shared memory through this one array (no static
@@ -91,7 +92,18 @@ constexpr int kRingGroupBytes = kCT * kRingBytesPerThread;
 constexpr int kYwOff = kRingOff + kGroups * kRingGroupBytes;               // [kGroups][kMaxCellRows] float2 (ya1, ya)
 constexpr int kScratchOff = kYwOff + kGroups * kMaxCellRows * 8;           // [kGroups][2 * kCWarps] words of the LUT build
 constexpr int kMiscOff = kScratchOff + kGroups * 2 * kCWarps * 4;          // [kGroups][kMiscWords]
-constexpr int kMiscWords = 8;                                              // ticket slots [2], look-ahead flags [2], flag, last
+// Two TMA experiments are kept behind compile-time switches (measured A/B in profiles/r02_clahe_notes.md; both lose):
+#ifndef NV12EQ_CLAHE_TMA
+#define NV12EQ_CLAHE_TMA 0   // 1: tile rows staged by the TMA unit (cp.async.bulk.tensor + mbarrier stages) instead of the per-thread cp.async ring
+#endif
+#ifndef NV12EQ_CLAHE_PF
+#define NV12EQ_CLAHE_PF 0    // 1: TMA L2 prefetch (cp.async.bulk.prefetch.tensor) of the next item's pixels when its ticket is drawn
+#endif
+constexpr bool kTmaTiles = NV12EQ_CLAHE_TMA != 0;
+constexpr bool kTmaPrefetch = NV12EQ_CLAHE_PF != 0;
+constexpr int kStages = 4;                                                 // TMA stages of a tile item (they live in the group's ring bytes)
+constexpr int kStageBytes = kRingGroupBytes / kStages;                     // 4 KB: at most one 16-byte piece per thread
+constexpr int kMiscWords = 8 + 4 * kStages;                                // ticket slots [2], look-ahead flags [2], flag, last, pad [2]; full / empty mbarriers
 constexpr int kClaheSmemBytes = kMiscOff + kGroups * kMiscWords * 4;       // dynamic shared memory of clahe_kernel
 
 struct ClaheParams {
@@ -123,6 +135,17 @@ struct ClaheParams {
     uint32_t* ticket;      // [1] self-cleaned
     uint32_t* status;      // [1]
     unsigned long long* trace;  // optional [items][4] (developer tool)
+    // TMA staging of the tile rows (tile items, NV12EQ_CLAHE_TMA): rank-3 maps (x bytes, row, frame) over the input batch with
+    // boxes of tma_bw x tma_bh bytes ([0]) and tma_bw x tma_bh_tail ([1], last stage of a tile when th % tma_bh != 0)
+    alignas(64) CUtensorMap tile_map[2];
+    int tma_tiles;              // 0: per-thread cp.async ring (any alignment / padding)
+    int tma_bw, tma_nb;         // box width in bytes, boxes per row block (tw = tma_bw * tma_nb)
+    int tma_bh, tma_bh_tail;    // rows per stage, rows of the last stage
+    int tma_nst;                // stages per tile
+    // L2 prefetch of the next item's pixels by the TMA unit (NV12EQ_CLAHE_PF): boxes of pf_bw x pf_bh bytes of the same rank-3
+    // view, issued by the group's thread 0 when it draws the next ticket, one item ahead of the loads
+    alignas(64) CUtensorMap pf_map;
+    int pf_on, pf_bw, pf_bh;
     uint32_t slot_magic;        // floor(2^32 / items per slot) + 1 if items * items_per_slot < 2^32 (exact division by multiply), else 0
     int debug_skip;             // developer tool: bit0 skip tile histogram, bit1 skip cell blend, bit2 skip uv, bit3 skip LUT build, bit4 skip table build
 };
@@ -266,6 +289,23 @@ struct GroupTickets {
                 const uint32_t g = p.slot_magic ? __umulhi(pending, p.slot_magic) : pending / per_slot;
                 const int r = (int)(pending - g * per_slot), f = (int)g - p.lag;
                 if (r >= T && r < T + I && f >= 0) pending_ready = ld_acquire_u32(p.tiles_done + f) >= (uint32_t)T;
+                if (kTmaPrefetch && p.pf_on) {
+                    int x0 = 0, y0 = 0, x1 = 0, y1 = 0, z = -1;
+                    if (r < T) {
+                        if ((int)g < p.n_frames) {
+                            const int tyi = small_div(r, p.tx), txi = r - tyi * p.tx;
+                            x0 = txi * p.tw; y0 = tyi * p.th; x1 = x0 + p.tw; y1 = y0 + p.th; z = (int)g;
+                        }
+                    } else if (r < T + I && f >= 0) {
+                        const int ci = r - T;
+                        const int cy = small_div(ci, p.nxc), cx = ci - cy * p.nxc;
+                        const int4 xc = p.cells_in_params ? p.xc_small[cx] : p.xcells[cx], yc = p.cells_in_params ? p.yc_small[cy] : p.ycells[cy];
+                        x0 = xc.x; x1 = xc.y; y0 = yc.x; y1 = yc.y; z = f;
+                    }
+                    if (z >= 0)
+                        for (int y = y0; y < y1; y += p.pf_bh)
+                            for (int x = x0; x < x1; x += p.pf_bw) tma_prefetch_3d(&p.pf_map, x, y, z);
+                }
             }
         }
     }
@@ -590,7 +630,7 @@ struct CellRows {
 };
 
 template <int MIN_CTAS>
-__global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const ClaheParams p) {
+__global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const __grid_constant__ ClaheParams p) {
     uint8_t* const rows = reinterpret_cast<uint8_t*>(nv12eq_smem_rows);   // see the shared memory map above
     const int group = threadIdx.x / kCT, tid = threadIdx.x - group * kCT, lane = tid & 31, warp = tid >> 5;
     const int bar = 1 + group;
@@ -615,6 +655,19 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const Cl
                                       : (uint32_t)(group * kHalfBytes + (lane & (kCellReps - 1)) * 8);
     const uint32_t yw_base = (uint32_t)(kYwOff + group * kMaxCellRows * 8);
 
+    // mbarriers of the group's TMA stages: full[s] (armed by thread 0 with the stage's bytes), empty[s] (one arrival per warp)
+    const uint32_t bar_full = kSmemBase + (uint32_t)(kMiscOff + (group * kMiscWords + 8) * 4);
+    const uint32_t bar_empty = bar_full + kStages * 8;
+    const uint32_t stage_base = (uint32_t)(kRingOff + group * kRingGroupBytes);     // offset from the start of the dynamic array
+    if (kTmaTiles && tid == 0) {
+#pragma unroll
+        for (int s_ = 0; s_ < kStages; ++s_) {
+            mbar_init(bar_full + s_ * 8, 1);
+            mbar_init(bar_empty + s_ * 8, kCWarps);
+        }
+        fence_mbar_init();
+    }
+    uint32_t tk = 0;   // TMA stage uses of this group since the kernel started (same value in all of its threads)
     GroupTickets q{p.ticket, s_ticket, tid, bar, p, total_items, (uint32_t)per_slot, T, I, 0u, 0u, 0u, false};
     q.start();
     int publish = -1;   // thread 0: frame whose tile counter still has to be bumped for the tile item just finished
@@ -659,9 +712,54 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const Cl
                 const int nrows = (vec16 && tr < rpp && tr < p.th) ? small_div(p.th - tr + rpp - 1, rpp) : 0;
                 const uint8_t* ptr = y + (size_t)(y0 + tr) * p.stride + x0 + tc * 16;
                 const size_t rstep = (size_t)rpp * p.stride;
+                bool tma_ok = true;
                 if (p.debug_skip & 1) {
                     hist256_zero(half, tid);
                     group_sync(bar);
+                } else if (kTmaTiles && p.tma_tiles) {
+                    // Rows staged by the TMA unit: stage k = rows [k * bh, k * bh + bh) of the tile as tma_nb boxes, kStages - 1
+                    // stages in flight.  A stage is a run of 16-byte pieces (any piece order gives the same histogram): thread t
+                    // takes piece pc of box bx in every stage.
+                    const int nst = p.tma_nst;
+                    const uint32_t tk0 = tk;
+                    const uint32_t box_slot = (uint32_t)(p.tma_bw * p.tma_bh + 127) & ~127u;   // a box lands on a 128-byte boundary
+                    auto issue_stage = [&](int k) {   // thread 0
+                        const uint32_t s_ = (tk0 + (uint32_t)k) % kStages;
+                        const bool tail = (k == nst - 1) && p.tma_bh_tail != p.tma_bh;
+                        const int bh = tail ? p.tma_bh_tail : p.tma_bh;
+                        mbar_arrive_expect_tx(bar_full + s_ * 8, (uint32_t)(p.tma_bw * bh * p.tma_nb));
+                        for (int b = 0; b < p.tma_nb; ++b)
+                            tma_load_3d(kSmemBase + stage_base + s_ * kStageBytes + (uint32_t)b * box_slot, &p.tile_map[tail ? 1 : 0], x0 + b * p.tma_bw,
+                                        y0 + k * p.tma_bh, g, bar_full + s_ * 8, keep);
+                    };
+                    if (tid == 0) {
+                        fence_proxy_async_smem();   // the ring bytes were last written by cp.async (generic proxy)
+                        for (int k = 0; k < kStages - 1 && k < nst; ++k) issue_stage(k);
+                    }
+                    hist256_zero(half, tid);
+                    group_sync(bar);
+                    const int ppb_full = (p.tma_bw * p.tma_bh) >> 4, ppb_tail = (p.tma_bw * p.tma_bh_tail) >> 4;   // pieces per box
+                    const int bx_f = small_div(tid, ppb_full), bx_t = small_div(tid, ppb_tail);
+                    const uint32_t off_full = (uint32_t)bx_f * box_slot + (uint32_t)(tid - bx_f * ppb_full) * 16u;
+                    const uint32_t off_tail = (uint32_t)bx_t * box_slot + (uint32_t)(tid - bx_t * ppb_tail) * 16u;
+#pragma unroll 1
+                    for (int k = 0; k < nst; ++k) {
+                        const uint32_t s_ = tk % kStages, par = (tk / kStages) & 1u;
+                        if (k + 2 >= nst) q.prefetch();
+                        if (!mbar_wait(bar_full + s_ * 8, par)) { tma_ok = false; break; }
+                        const bool last = k == nst - 1;
+                        if ((last ? bx_t : bx_f) < p.tma_nb) hist256_vec(lds128_rel(stage_base + s_ * kStageBytes + (last ? off_tail : off_full)), lane4);
+                        // The increments above could not issue before their piece arrived in registers, and this arrival issues after
+                        // them: the stage may be overwritten once every warp has arrived.
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_empty + s_ * 8);
+                        if (tid == 0 && k + kStages - 1 < nst) {
+                            // refill the stage of the previous iteration (all warps are done with it, or about to be)
+                            if (k >= 1 && !mbar_wait(bar_empty + ((tk - 1) % kStages) * 8, ((tk - 1) / kStages) & 1u)) tma_ok = false;
+                            else issue_stage(k + kStages - 1);
+                        }
+                        ++tk;
+                    }
                 } else if (vec16) {
                     TileRowsRing t;
                     t.start(ptr, rstep, nrows, tid, group);   // the first loads leave before the table is zeroed
@@ -679,6 +777,10 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const Cl
                         for (int x = max(x0, p.w) + lane; x < x0 + p.tw; x += 32)
                             hist256_byte(src_row[reflect101(x, p.w)], lane4);
                     }
+                }
+                if (!tma_ok) {   // a stage never arrived: report and stop (the host resets the workspace)
+                    atomicExch(p.status, 3u);
+                    break;
                 }
                 q.prefetch();  // the row sums and the LUT build hide the ticket round trip
                 group_sync(bar);

@@ -376,6 +376,44 @@ __device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) {
     return r;
 }
 
+// ---- mbarrier + TMA (cp.async.bulk.tensor) ---------------------------------------------------------------------
+// `bar` / `dst` are shared-window addresses (smem_u32).  One elected thread arms a barrier with the byte count of the boxes it
+// requests (arrive.expect_tx); the TMA unit completes the transaction bytes as the boxes land; consumers wait on the phase
+// parity.  No registers and no issue slots of the consuming warps are spent on the copy itself.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    // the time hint lets the hardware park the warp until the phase completes (no issue slots burnt on polling)
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+    return ok != 0;
+}
+// Bounded wait (a lost transaction must not hang the device): false after ~2 s.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > (4ll << 30)) return false;
+    return true;
+}
+// One box of a rank-3 tensor map (x = bytes along a row, y = row, z = frame) into shared memory
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, int x, int y, int z, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar), "l"(policy) : "memory");
+}
+
+// L2 prefetch of one box (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const void* map, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // ---- warp scan ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll

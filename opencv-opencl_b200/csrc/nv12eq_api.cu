@@ -451,6 +451,33 @@ void axis_cells(int n, float inv, int ntiles, int max_len, int align, std::vecto
 #define NV12EQ_CLAHE_UV_CHUNK (128 << 10)
 #endif
 constexpr unsigned long long kUvChunk = NV12EQ_CLAHE_UV_CHUNK;   // chroma bytes per uv item (512 KB items measured 7 % slower at 1080p, equal at 4K)
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the library does not link libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<TensorMapEncodeFn>(f);
+    }();
+    return fn;
+}
+// Rank-3 byte tensor (x, row, frame) over a batch of planes, box bw x bh x 1, no swizzle.
+bool encode_plane_map(CUtensorMap* m, const void* base, int w, int h, int n, size_t stride, size_t pitch, int bw, int bh) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)pitch};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d_out, int n, size_t pitch, int w, int h,
                  int stride, double clip, int tx, int ty, int uv_mode, cudaStream_t st) {
     if (n == 0) return NV12EQ_OK;
@@ -510,6 +537,36 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     p.status = ws_status(ws);
     if (const char* dbg = getenv("NV12EQ_DEBUG_SKIP")) p.debug_skip = atoi(dbg);
 
+    // Tile rows through the TMA unit when the layout allows it (16-byte aligned planes and tile columns, tiles inside the image);
+    // NV12EQ_CLAHE_TMA=0 keeps the per-thread cp.async ring (A/B tool).
+    {
+        const char* e = getenv("NV12EQ_CLAHE_TMA");
+        const bool want = !(e && e[0] == '0');
+        const int tw = g.tw, th = g.th;
+        const int nb = (tw + 255) / 256;
+        // L2 prefetch boxes: a tile is nb x nrb boxes (any 16-byte aligned layout; boxes may overshoot a border cell into its
+        // neighbour, which another item is about to read anyway)
+        const char* epf = getenv("NV12EQ_CLAHE_PF");
+        if (kTmaPrefetch && !(epf && epf[0] == '0') && !p.padded && ((uintptr_t)d_in & 15) == 0 && stride % 16 == 0 && pitch % 16 == 0) {
+            const int nbx = (tw + 255) / 256, nby = (th + 255) / 256;
+            const int bwp = std::min(w, (((tw + nbx - 1) / nbx) + 15) & ~15), bhp = (th + nby - 1) / nby;
+            if (bwp % 16 == 0 && bwp <= 256 && encode_plane_map(&p.pf_map, d_in, w, h, n, (size_t)stride, pitch, bwp, bhp)) {
+                p.pf_on = 1; p.pf_bw = bwp; p.pf_bh = bhp;
+            }
+        }
+        if (kTmaTiles && want && !p.padded && ((uintptr_t)d_in & 15) == 0 && stride % 16 == 0 && pitch % 16 == 0 && tw % 16 == 0 && tw <= kStageBytes &&
+            tw % nb == 0 && (tw / nb) % 16 == 0) {
+            const int bw = tw / nb;
+            // rows per stage: the boxes of a stage (each on a 128-byte boundary) fit the stage, at most one 16-byte piece per thread
+            int bh = std::max(1, std::min(std::min(256, kStageBytes / tw), th));
+            while (bh > 1 && (((bw * bh + 127) & ~127) * (nb - 1) + bw * bh > kStageBytes || nb * ((bw * bh) >> 4) > kCT)) --bh;
+            const int nst = (th + bh - 1) / bh;
+            const int tail = th - (nst - 1) * bh;
+            bool ok = encode_plane_map(&p.tile_map[0], d_in, w, h, n, (size_t)stride, pitch, bw, bh);
+            if (ok && tail != bh) ok = encode_plane_map(&p.tile_map[1], d_in, w, h, n, (size_t)stride, pitch, bw, tail);
+            if (ok) { p.tma_tiles = 1; p.tma_bw = bw; p.tma_nb = nb; p.tma_bh = bh; p.tma_bh_tail = tail; p.tma_nst = nst; }
+        }
+    }
     const long long per_slot = (long long)T + (long long)p.nxc * p.nyc + U;
     // CTAs per SM: four 64-register CTAs, or three with 80 registers (no rematerialisation in the blend loop).  Measured on
     // 4K frames with cool-downs between runs (tools/sweep.py --ctas 4,3,4,3 --cooldown 4): 8x8 grid (130 K-pixel tiles) 7.22 vs
