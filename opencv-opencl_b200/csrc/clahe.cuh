@@ -192,6 +192,12 @@ __device__ __forceinline__ int4 lds128_rel(uint32_t off) {
 __device__ __forceinline__ void cp_async8_rel(uint32_t off, const void* g) {
     asm volatile("cp.async.ca.shared.global [%0+" NV12EQ_SBASE "], [%1], 8;" ::"r"(off), "l"(g) : "memory");
 }
+#ifndef NV12EQ_CLAHE_L2HINT
+#define NV12EQ_CLAHE_L2HINT 1   // tile pass loads carry L2::evict_last (the cell pass reads the plane again `lag` frames later)
+#endif
+__device__ __forceinline__ void cp_async16_rel_hint(uint32_t off, const void* g, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0+" NV12EQ_SBASE "], [%1], 16, %2;" ::"r"(off), "l"(g), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async16_rel(uint32_t off, const void* g) {
     asm volatile("cp.async.cg.shared.global [%0+" NV12EQ_SBASE "], [%1], 16;" ::"r"(off), "l"(g) : "memory");
 }
@@ -348,11 +354,19 @@ struct TileRowsRing {
     size_t rstep;
     int nrows;
     uint32_t ring0;
-    __device__ __forceinline__ void start(const uint8_t* __restrict__ ptr, size_t rstep_, int nrows_, int tid, int group) {
-        rstep = rstep_; nrows = nrows_; ring0 = (uint32_t)(kRingOff + group * kRingGroupBytes + tid * 16);
+    uint64_t pol;   // L2 eviction policy of the loads
+    __device__ __forceinline__ void load(uint32_t off, const uint8_t* g) const {
+#if NV12EQ_CLAHE_L2HINT
+        cp_async16_rel_hint(off, g, pol);
+#else
+        cp_async16_rel(off, g);
+#endif
+    }
+    __device__ __forceinline__ void start(const uint8_t* __restrict__ ptr, size_t rstep_, int nrows_, int tid, int group, uint64_t pol_) {
+        rstep = rstep_; nrows = nrows_; ring0 = (uint32_t)(kRingOff + group * kRingGroupBytes + tid * 16); pol = pol_;
 #pragma unroll
         for (int j = 0; j < D - 1; ++j) {
-            if (j < nrows) cp_async16_rel(ring0 + (uint32_t)j * kSlotStride, ptr + (size_t)j * rstep);
+            if (j < nrows) load(ring0 + (uint32_t)j * kSlotStride, ptr + (size_t)j * rstep);
             cp_async_commit();
         }
         pn = ptr + (size_t)(D - 1) * rstep;
@@ -364,7 +378,7 @@ struct TileRowsRing {
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 if (i0 + j < nrows) {
-                    if (i0 + j + D - 1 < nrows) cp_async16_rel(ring0 + (uint32_t)((j + D - 1) % D) * kSlotStride, pn);
+                    if (i0 + j + D - 1 < nrows) load(ring0 + (uint32_t)((j + D - 1) % D) * kSlotStride, pn);
                     cp_async_commit();
                     cp_async_wait<D - 1>();
                     hist256_vec(lds128_rel(ring0 + (uint32_t)j * kSlotStride), lane4);
@@ -762,7 +776,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const __
                     }
                 } else if (vec16) {
                     TileRowsRing t;
-                    t.start(ptr, rstep, nrows, tid, group);   // the first loads leave before the table is zeroed
+                    t.start(ptr, rstep, nrows, tid, group, keep);   // the first loads leave before the table is zeroed
                     hist256_zero(half, tid);
                     group_sync(bar);
                     t.run(lane4, q);

@@ -148,6 +148,10 @@ struct ColorEqParams {
     uint32_t* ticket;
     uint32_t* status;
 };
+#ifndef NV12EQ_COLOR_BULK
+#define NV12EQ_COLOR_BULK 0   // 1: a warp round arrives as ONE bulk copy of the TMA unit (cp.async.bulk + mbarrier) that carries an L2 policy;
+#endif                        // 0: three 16-byte cp.async per lane (no policy: ptxas 12.9 miscompiles cp.async with a cache hint here)
+constexpr bool kColorBulk = NV12EQ_COLOR_BULK != 0;
 constexpr int kColorRingDepth = 3;                       // warp rounds in flight
 constexpr int kColorRoundBytes = 1536;                   // 512 pixels
 constexpr int kColorRingBytes = kWarps * kColorRingDepth * kColorRoundBytes;
@@ -210,9 +214,19 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) color_equalize_kernel(cons
     __shared__ __align__(16) uint8_t s_lut[256];
     __shared__ uint32_t s_ticket[2];
     __shared__ int s_flag;
+    __shared__ __align__(8) unsigned long long s_bar[kWarps * kColorRingDepth];   // one mbarrier per warp and ring stage (bulk copies)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lane_base = smem_u32(smem) + lane * 4;
+    const uint32_t bars = smem_u32(s_bar) + (uint32_t)warp * (kColorRingDepth * 8);
+    if (kColorBulk) {
+        if (lane < kColorRingDepth) mbar_init(bars + lane * 8, 1);
+        fence_mbar_init();
+        __syncwarp();
+    }
+    uint32_t seq = 0;   // warp rounds this warp has consumed since the kernel started: stage = seq % depth, phase parity = (seq / depth) & 1
+    // The first pass keeps the frame in L2 for the second one (evict_last), the second pass and the stores let go of it.
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
     const uint32_t ring = smem_u32(smem) + kLaneTableBytes + (uint32_t)warp * (kColorRingDepth * kColorRoundBytes);
     const int C = p.chunks;
     const int lag = p.lag;
@@ -235,7 +249,19 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) color_equalize_kernel(cons
         const long long nr = rd1 > rd0 + warp ? (long long)((rd1 - rd0 - warp + kWarps - 1) / kWarps) : 0;
 
         // issue the three 16-byte pieces of this lane for warp round `k` (0-based within the item) into ring stage k % depth
+        const uint32_t seq0 = seq;
         auto issue = [&](const uint8_t* frame, long long k) {
+            if (kColorBulk) {
+                if (k < nr && lane == 0) {
+                    const unsigned long long round = rd0 + warp + (unsigned long long)k * kWarps;
+                    const unsigned long long b0 = round * kColorRoundBytes, bend = p.npx * 3;
+                    const uint32_t bytes = (uint32_t)min((unsigned long long)kColorRoundBytes, bend - b0);
+                    const uint32_t sq = seq0 + (uint32_t)k, stg = sq % kColorRingDepth;
+                    mbar_arrive_expect_tx(bars + stg * 8, bytes);
+                    bulk_load(ring + stg * kColorRoundBytes, frame + b0, bytes, bars + stg * 8, hist_item ? pol_keep : pol_drop);
+                }
+                return;
+            }
             if (k < nr) {
                 const unsigned long long round = rd0 + warp + (unsigned long long)k * kWarps;
                 const unsigned long long v0 = round * 96;  // first 16-byte piece of the round
@@ -259,11 +285,16 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) color_equalize_kernel(cons
             for (long long k = 0; k < nr; ++k) {
                 if (k + 2 >= nr) q.prefetch();  // late: an early draw would queue the next item behind this one
                 issue(frame, k + kColorRingDepth - 1);
-                cp_async_wait<kColorRingDepth - 1>();
+                const uint32_t sq = seq0 + (uint32_t)k, stg = kColorBulk ? sq % kColorRingDepth : (uint32_t)(k % kColorRingDepth);
+                if (kColorBulk) {
+                    if (!mbar_wait(bars + stg * 8, (sq / kColorRingDepth) & 1u)) atomicExch(p.status, 3u);
+                } else {
+                    cp_async_wait<kColorRingDepth - 1>();
+                }
                 __syncwarp();
                 const unsigned long long px0 = (rd0 + warp + (unsigned long long)k * kWarps) * 512 + (unsigned long long)lane * 16;
                 if (px0 < p.npx) {
-                    const uint32_t st = ring + (uint32_t)(k % kColorRingDepth) * kColorRoundBytes + (uint32_t)lane * 48u;
+                    const uint32_t st = ring + stg * kColorRoundBytes + (uint32_t)lane * 48u;
                     const int4 a = lds_s4(st), b = lds_s4(st + 16), cc = lds_s4(st + 32);
                     const uint32_t qw[12] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y,
                                              (uint32_t)b.z, (uint32_t)b.w, (uint32_t)cc.x, (uint32_t)cc.y, (uint32_t)cc.z, (uint32_t)cc.w};
@@ -276,8 +307,9 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) color_equalize_kernel(cons
                         red_shared_inc(lane_base + (opaque(bgr_luma14(bgr_px<3>(q0, q1, q2)) >> 14) << 7));
                     }
                 }
-                __syncwarp();  // the stage is re-filled two rounds from now by this warp's own cp.asyncs
+                __syncwarp();  // the stage is re-filled two rounds from now by this warp's own copies
             }
+            seq += (uint32_t)nr;
             __syncthreads();
             if (tid < 256) {
                 const uint32_t cnt = lane_table_row_sum(smem, tid);
@@ -329,12 +361,17 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) color_equalize_kernel(cons
             for (long long k = 0; k < nr; ++k) {
                 if (k + 2 >= nr) q.prefetch();
                 issue(frame, k + kColorRingDepth - 1);
-                cp_async_wait<kColorRingDepth - 1>();
+                const uint32_t sq = seq0 + (uint32_t)k, stg = kColorBulk ? sq % kColorRingDepth : (uint32_t)(k % kColorRingDepth);
+                if (kColorBulk) {
+                    if (!mbar_wait(bars + stg * 8, (sq / kColorRingDepth) & 1u)) atomicExch(p.status, 3u);
+                } else {
+                    cp_async_wait<kColorRingDepth - 1>();
+                }
                 __syncwarp();
                 const unsigned long long round = rd0 + warp + (unsigned long long)k * kWarps;
                 const unsigned long long px0 = round * 512 + (unsigned long long)lane * 16;
                 if (px0 < p.npx) {
-                    const uint32_t st = ring + (uint32_t)(k % kColorRingDepth) * kColorRoundBytes + (uint32_t)lane * 48u;
+                    const uint32_t st = ring + stg * kColorRoundBytes + (uint32_t)lane * 48u;
                     const int4 a = lds_s4(st), b = lds_s4(st + 16), cc = lds_s4(st + 32);
                     const uint32_t qw[12] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w, (uint32_t)b.x, (uint32_t)b.y,
                                              (uint32_t)b.z, (uint32_t)b.w, (uint32_t)cc.x, (uint32_t)cc.y, (uint32_t)cc.z, (uint32_t)cc.w};
@@ -369,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) color_equalize_kernel(cons
                 }
                 __syncwarp();
             }
+            seq += (uint32_t)nr;
         }
         q.advance();
     }

@@ -409,6 +409,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, int x
                  ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar), "l"(policy) : "memory");
 }
 
+// 1-D bulk copy global -> shared through the TMA unit (src, dst and size multiples of 16 bytes), with an L2 eviction policy
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
 // L2 prefetch of one box (no shared memory, no barrier)
 __device__ __forceinline__ void tma_prefetch_3d(const void* map, int x, int y, int z) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");

@@ -640,6 +640,7 @@ int launch_color_fused(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint
     long long lag = (10ll * ctas + 16 * 2 * C - 1) / (10 * 2 * C);
     lag = std::min<long long>(lag, 8);
     if (ctx->tune_lag > 0) lag = ctx->tune_lag;
+    if (ctx->tune_lag < 0) lag = 0;   // apply items of a frame directly behind its histogram items (the frame is still in L2; CTAs wait at the switch)
     p.lag = (int)std::min<long long>(lag, std::max(n - 1, 0));
     if (mode == COLOR_YUV) { p.kB = 8061; p.kR = 14369; p.iB = 33292; p.iG1 = -6472; p.iG2 = -9519; p.iR = 18678; }
     else { p.kB = 9241; p.kR = 11682; p.iB = 29049; p.iG1 = -5636; p.iG2 = -11698; p.iR = 22987; }

@@ -21,16 +21,21 @@ ap.add_argument("--ctas", type=int, default=0)
 ap.add_argument("--schedule", type=int, default=0)
 a = ap.parse_args()
 W, H = SIZES[a.size]
-n, pitch = a.frames, nv12eq.nv12_frame_bytes(W, H)
+n, pitch = a.frames, (3 * W * H if a.op == "color" else nv12eq.nv12_frame_bytes(W, H))
 ctx = nv12eq.Context(0, W, H, 1)
 ctx.set_tuning(a.chunks, a.lag, a.ctas, a.schedule)
 st = torch.cuda.current_stream()
 d_in = torch.empty(n * pitch, dtype=torch.uint8, device="cuda")
 d_out = torch.empty_like(d_in)
-ctx.synth_nv12_device(d_in, n, pitch, W, H, stream=st)
+if a.op == "color":
+    ctx.synth_bgr_device(d_in, n, pitch, W, H, stream=st)
+else:
+    ctx.synth_nv12_device(d_in, n, pitch, W, H, stream=st)
 for _ in range(a.launches):
     if a.op == "equalize":
         ctx.equalize_hist_device(d_in, d_out, n, pitch, W, H, stream=st)
+    elif a.op == "color":
+        ctx.color_equalize_device(d_in, d_out, n, pitch, W, H, stream=st)
     else:
         ctx.clahe_device(d_in, d_out, n, pitch, W, H, 2.0, (8, 8), stream=st)
 torch.cuda.synchronize()
