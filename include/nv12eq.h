@@ -24,6 +24,7 @@
  *                                          packed planes)
  *   nv12eq_clahe16* / nv12eq_p010_clahe <- cv::CLAHE::apply on CV_16UC1 (65536 bins), the 16-bit path of clahevideo.cpp:195's
  *                                          operator for P010 decoders
+ *   nv12eq_nv12_to_bgr / bgr_to_nv12    <- cvtColor(COLOR_YUV2BGR_NV12) for display / the I420 arithmetic with interleaved chroma
  *   nv12eq_bgr_to_i420 / _device        <- cvtColor(bgr, COLOR_BGR2YUV_I420) in front of the Y-plane operator,
  *                                          1frameMeasure.cpp:32-35
  *   nv12eq_get_counters                 <- the Counters struct + status tick, OpenCLequalHist.cpp:45-61,439-508
@@ -204,6 +205,21 @@ int nv12eq_color_clahe_device(nv12eq_ctx* ctx, const uint8_t* d_bgr_in, uint8_t*
 int nv12eq_bgr_to_i420(nv12eq_ctx* ctx, const uint8_t* bgr, int width, int height, int stride, uint8_t* out, size_t out_size);
 int nv12eq_bgr_to_i420_device(nv12eq_ctx* ctx, const uint8_t* d_bgr, uint8_t* d_out, int n_frames, size_t bgr_pitch,
                               size_t out_pitch, int width, int height, int stride, void* cuda_stream);
+
+/* ---- NV12 <-> BGR adapters --------------------------------------------------------------
+ * nv12_to_bgr = cvtColor(nv12, COLOR_YUV2BGR_NV12): the display-side inverse of the NV12 path (the reference's still-image tools
+ * convert back with cvtColor, singlecolor.cpp:66 / clahe1frame.cpp:102; its pipelines hand NV12 to the encoder).
+ * bgr_to_nv12 = the arithmetic of COLOR_BGR2YUV_I420 (1frameMeasure.cpp:32) with the chroma planes interleaved (U first): the
+ * frame the NV12 operators above take.  width and height must be even.  `stride` is the NV12 row stride (chroma rows at
+ * stride * height), `bgr_stride` the BGR row stride, both in bytes; pitches are bytes between frames. */
+int nv12eq_nv12_to_bgr(nv12eq_ctx* ctx, const uint8_t* nv12, size_t nv12_size, int width, int height, int stride, uint8_t* bgr,
+                       size_t bgr_size, int bgr_stride);
+int nv12eq_bgr_to_nv12(nv12eq_ctx* ctx, const uint8_t* bgr, size_t bgr_size, int width, int height, int bgr_stride, uint8_t* nv12,
+                       size_t nv12_size, int stride);
+int nv12eq_nv12_to_bgr_device(nv12eq_ctx* ctx, const uint8_t* d_nv12, uint8_t* d_bgr, int n_frames, size_t nv12_pitch,
+                              size_t bgr_pitch, int width, int height, int stride, int bgr_stride, void* cuda_stream);
+int nv12eq_bgr_to_nv12_device(nv12eq_ctx* ctx, const uint8_t* d_bgr, uint8_t* d_nv12, int n_frames, size_t bgr_pitch,
+                              size_t nv12_pitch, int width, int height, int bgr_stride, int stride, void* cuda_stream);
 
 /* ---- 16-bit planes: CLAHE on CV_16UC1 (P010 / 16-bit, histSize 65536) -------------------
  * cv::CLAHE::apply accepts CV_16UC1 with 65536-bin tile histograms; the reference only calls it on 8-bit Y planes

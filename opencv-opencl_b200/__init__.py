@@ -130,6 +130,10 @@ _SIGNATURES = {
     "nv12eq_p010_clahe": (_c_int, [_c_vp, _c_vp, _c_sz, _c_vp, _c_sz, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int, _c_int]),
     "nv12eq_bgr_to_i420": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_vp, _c_sz]),
     "nv12eq_bgr_to_i420_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_sz, _c_int, _c_int, _c_int, _c_vp]),
+    "nv12eq_nv12_to_bgr": (_c_int, [_c_vp, _c_vp, _c_sz, _c_int, _c_int, _c_int, _c_vp, _c_sz, _c_int]),
+    "nv12eq_bgr_to_nv12": (_c_int, [_c_vp, _c_vp, _c_sz, _c_int, _c_int, _c_int, _c_vp, _c_sz, _c_int]),
+    "nv12eq_nv12_to_bgr_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "nv12eq_bgr_to_nv12_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_sz, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "nv12eq_stream_open": (_c_int, [_c_vp, ctypes.POINTER(StreamConfig), ctypes.POINTER(_c_vp)]),
     "nv12eq_stream_push": (_c_int, [_c_vp, _c_vp, _c_sz, ctypes.POINTER(ctypes.c_uint64)]),
     "nv12eq_stream_pop": (_c_int, [_c_vp, _c_vp, _c_sz, ctypes.POINTER(ctypes.c_uint64), _c_int]),
@@ -481,6 +485,37 @@ class Context:
         stride = 3 * width if stride is None else stride
         self._check(self._lib.nv12eq_bgr_to_i420_device(self._h, _ptr(d_bgr), _ptr(d_out), n_frames, bgr_pitch, out_pitch, width,
                                                         height, stride, _stream_ptr(stream)))
+
+    # -- NV12 <-> BGR adapters -------------------------------------------------------------------------
+    def nv12_to_bgr(self, nv12: np.ndarray, width: int, height: int, stride: Optional[int] = None, out=None) -> np.ndarray:
+        """``cv2.cvtColor(nv12, COLOR_YUV2BGR_NV12)``: flat NV12 frame -> (H, W, 3) BGR (display side of the NV12 path)."""
+        stride = width if stride is None else stride
+        out = np.empty((height, width, 3), np.uint8) if out is None else out
+        span = out.strides[0] * (height - 1) + 3 * width   # bytes from the first to the last pixel (rows may be strided views)
+        self._check(self._lib.nv12eq_nv12_to_bgr(self._h, _ptr(nv12), _nbytes(nv12), width, height, stride, _ptr(out), span,
+                                                 out.strides[0]))
+        return out
+
+    def bgr_to_nv12(self, bgr: np.ndarray, stride: Optional[int] = None, out=None) -> np.ndarray:
+        """BGR -> flat NV12 frame (COLOR_BGR2YUV_I420 arithmetic, chroma interleaved U first): the input of the NV12 operators."""
+        h, w, _ = bgr.shape
+        stride = w if stride is None else stride
+        out = np.empty(stride * (h + h // 2), np.uint8) if out is None else out
+        self._check(self._lib.nv12eq_bgr_to_nv12(self._h, _ptr(bgr), bgr.strides[0] * (h - 1) + 3 * w, w, h, bgr.strides[0], _ptr(out),
+                                                 _nbytes(out), stride))
+        return out
+
+    def nv12_to_bgr_device(self, d_nv12, d_bgr, n_frames, nv12_pitch, bgr_pitch, width, height, stride=None, bgr_stride=None, stream=None):
+        stride = width if stride is None else stride
+        bgr_stride = 3 * width if bgr_stride is None else bgr_stride
+        self._check(self._lib.nv12eq_nv12_to_bgr_device(self._h, _ptr(d_nv12), _ptr(d_bgr), n_frames, nv12_pitch, bgr_pitch, width, height,
+                                                        stride, bgr_stride, _stream_ptr(stream)))
+
+    def bgr_to_nv12_device(self, d_bgr, d_nv12, n_frames, bgr_pitch, nv12_pitch, width, height, bgr_stride=None, stride=None, stream=None):
+        stride = width if stride is None else stride
+        bgr_stride = 3 * width if bgr_stride is None else bgr_stride
+        self._check(self._lib.nv12eq_bgr_to_nv12_device(self._h, _ptr(d_bgr), _ptr(d_nv12), n_frames, bgr_pitch, nv12_pitch, width, height,
+                                                        bgr_stride, stride, _stream_ptr(stream)))
 
     # -- synthetic inputs -------------------------------------------------------------------------------
     def synth_nv12_device(self, d_out, n_frames, frame_pitch, width, height, stride=None, seed=2026, first_frame=0,

@@ -476,4 +476,113 @@ __global__ void __launch_bounds__(kColorThreads) bgr_to_i420_kernel(const I420Pa
     }
 }
 
+// ---- NV12 <-> BGR adapters ----------------------------------------------------------------
+// nv12_to_bgr_kernel: cvtColor(nv12, COLOR_YUV2BGR_NV12), OpenCV's YUV420sp2RGB (Q20 limited-range BT.601, one chroma pair per
+// 2x2 block, saturating) -- the display-side inverse of the NV12 path; the reference's still-image tools convert back with
+// cvtColor at singlecolor.cpp:66 / clahe1frame.cpp:102.  bgr_to_nv12_kernel: the arithmetic of bgr_to_i420_kernel with the chroma
+// interleaved (U first), i.e. the frame the NV12 operators take.  One thread converts a 4x2 pixel block.
+struct Nv12BgrParams {
+    const uint8_t* in; uint8_t* out;
+    unsigned long long in_pitch, out_pitch;   // bytes between frames
+    int w, h;                                 // even
+    int nv12_stride, bgr_stride;              // bytes per row
+};
+__device__ __forceinline__ uint32_t sat_u8(int v) { return (uint32_t)min(max(v, 0), 255); }
+// one pixel: luma byte + chroma terms -> {B, G, R} in the low three bytes
+__device__ __forceinline__ uint32_t nv12_px(uint32_t y, int ruv, int guv, int buv) {
+    const int yy = (int)(y > 16u ? y - 16u : 0u) * 1220542;
+    return sat_u8((yy + buv) >> 20) | (sat_u8((yy + guv) >> 20) << 8) | (sat_u8((yy + ruv) >> 20) << 16);
+}
+__global__ void __launch_bounds__(kColorThreads) nv12_to_bgr_kernel(const Nv12BgrParams p) {
+    const int f = blockIdx.y;
+    const uint8_t* Y = p.in + (unsigned long long)f * p.in_pitch;
+    const uint8_t* UV = Y + (size_t)p.nv12_stride * p.h;
+    uint8_t* dst = p.out + (unsigned long long)f * p.out_pitch;
+    const int bw = (p.w + 3) / 4, bh = p.h / 2;          // 4x2 blocks (the last block of a row may be 2 wide)
+    const long long nblk = (long long)bw * bh;
+    const bool vec = ((p.w & 3) == 0) && ((p.nv12_stride & 3) == 0) && ((p.bgr_stride & 3) == 0) && ((((uintptr_t)Y | (uintptr_t)dst) & 3) == 0);
+    for (long long b = (long long)blockIdx.x * kColorThreads + threadIdx.x; b < nblk; b += (long long)gridDim.x * kColorThreads) {
+        const int by = (int)(b / bw), bx = (int)(b - (long long)by * bw);
+        const int x = bx * 4, y = by * 2;
+        const int xe = min(x + 4, p.w);
+        uint32_t uvw;
+        if (vec) uvw = __ldg(reinterpret_cast<const uint32_t*>(UV + (size_t)by * p.nv12_stride + x));
+        else {
+            const uint8_t* q = UV + (size_t)by * p.nv12_stride + x;
+            uvw = q[0] | (q[1] << 8);
+            if (xe - x > 2) uvw |= (q[2] << 16) | (q[3] << 24);
+        }
+        int ruv[2], guv[2], buv[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int u = (int)((uvw >> (16 * k)) & 255u) - 128, v = (int)((uvw >> (16 * k + 8)) & 255u) - 128;
+            ruv[k] = (1 << 19) + 1673527 * v;
+            guv[k] = (1 << 19) - 852492 * v - 409993 * u;
+            buv[k] = (1 << 19) + 2116026 * u;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint8_t* yrow = Y + (size_t)(y + r) * p.nv12_stride + x;
+            uint8_t* d = dst + (size_t)(y + r) * p.bgr_stride + 3 * (size_t)x;
+            if (vec) {
+                const uint32_t yw = __ldg(reinterpret_cast<const uint32_t*>(yrow));
+                const uint32_t p0 = nv12_px(yw & 255u, ruv[0], guv[0], buv[0]), p1 = nv12_px((yw >> 8) & 255u, ruv[0], guv[0], buv[0]);
+                const uint32_t p2 = nv12_px((yw >> 16) & 255u, ruv[1], guv[1], buv[1]), p3 = nv12_px(yw >> 24, ruv[1], guv[1], buv[1]);
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+                d32[0] = p0 | (p1 << 24);
+                d32[1] = (p1 >> 8) | (p2 << 16);
+                d32[2] = (p2 >> 16) | (p3 << 8);
+            } else {
+                for (int c = x; c < xe; ++c) {
+                    const int k = (c - x) >> 1;
+                    const uint32_t px = nv12_px(yrow[c - x], ruv[k], guv[k], buv[k]);
+                    uint8_t* o = d + 3 * (c - x);
+                    o[0] = (uint8_t)px; o[1] = (uint8_t)(px >> 8); o[2] = (uint8_t)(px >> 16);
+                }
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(kColorThreads) bgr_to_nv12_kernel(const Nv12BgrParams p) {
+    const int f = blockIdx.y;
+    const uint8_t* src = p.in + (unsigned long long)f * p.in_pitch;
+    uint8_t* Y = p.out + (unsigned long long)f * p.out_pitch;
+    uint8_t* UV = Y + (size_t)p.nv12_stride * p.h;
+    const int bw = (p.w + 3) / 4, bh = p.h / 2;
+    const long long nblk = (long long)bw * bh;
+    const bool vec = ((p.w & 3) == 0) && ((p.nv12_stride & 3) == 0) && ((p.bgr_stride & 3) == 0) && ((((uintptr_t)Y | (uintptr_t)src) & 3) == 0);
+    for (long long b = (long long)blockIdx.x * kColorThreads + threadIdx.x; b < nblk; b += (long long)gridDim.x * kColorThreads) {
+        const int by = (int)(b / bw), bx = (int)(b - (long long)by * bw);
+        const int x = bx * 4, y = by * 2;
+        if (vec) {
+            uint32_t uvw = 0;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + (size_t)(y + r) * p.bgr_stride + 3 * (size_t)x);
+                const uint32_t a = __ldg(s32), bb = __ldg(s32 + 1), c = __ldg(s32 + 2);
+                const int B0 = a & 255, G0 = (a >> 8) & 255, R0 = (a >> 16) & 255;
+                const int B1 = a >> 24, G1 = bb & 255, R1 = (bb >> 8) & 255;
+                const int B2 = (bb >> 16) & 255, G2 = bb >> 24, R2 = c & 255;
+                const int B3 = (c >> 8) & 255, G3 = (c >> 16) & 255, R3 = c >> 24;
+                *reinterpret_cast<uint32_t*>(Y + (size_t)(y + r) * p.nv12_stride + x) =
+                    i420_luma(B0, G0, R0) | (i420_luma(B1, G1, R1) << 8) | (i420_luma(B2, G2, R2) << 16) | (i420_luma(B3, G3, R3) << 24);
+                if (r == 0) uvw = i420_u(B0, G0, R0) | (i420_v(B0, G0, R0) << 8) | (i420_u(B2, G2, R2) << 16) | (i420_v(B2, G2, R2) << 24);
+            }
+            *reinterpret_cast<uint32_t*>(UV + (size_t)by * p.nv12_stride + x) = uvw;
+        } else {
+            const int xe = min(x + 4, p.w);
+            for (int r = 0; r < 2; ++r)
+                for (int c = x; c < xe; ++c) {
+                    const uint8_t* px = src + (size_t)(y + r) * p.bgr_stride + 3 * (size_t)c;
+                    Y[(size_t)(y + r) * p.nv12_stride + c] = (uint8_t)i420_luma(px[0], px[1], px[2]);
+                    if (r == 0 && !(c & 1)) {
+                        uint8_t* d = UV + (size_t)by * p.nv12_stride + c;
+                        d[0] = (uint8_t)i420_u(px[0], px[1], px[2]);
+                        d[1] = (uint8_t)i420_v(px[0], px[1], px[2]);
+                    }
+                }
+        }
+    }
+}
+
 }  // namespace nv12eq

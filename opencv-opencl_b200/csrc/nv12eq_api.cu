@@ -1548,6 +1548,88 @@ int nv12eq_bgr_to_i420(nv12eq_ctx* ctx, const uint8_t* bgr, int width, int heigh
     return NV12EQ_OK;
 }
 
+// ---- NV12 <-> BGR adapters ------------------------------------------------------------------------------
+static size_t nv12_frame_bytes(int stride, int h) { return (size_t)stride * (size_t)(h + h / 2); }
+static int check_nv12_bgr(nv12eq_ctx* ctx, int w, int h, int stride, int bgr_stride) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (w <= 0 || h <= 0 || stride < w || bgr_stride < 3 * w)
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad geometry w=%d h=%d stride=%d bgr_stride=%d", w, h, stride, bgr_stride);
+    if ((w & 1) || (h & 1)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "NV12 <-> BGR needs even width and height, got %dx%d", w, h);
+    if ((long long)w * h >= (1ll << 31)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "frame has 2^31 pixels or more");
+    if (w > ctx->max_w || h > ctx->max_h) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "frame %dx%d exceeds context maximum %dx%d", w, h, ctx->max_w, ctx->max_h);
+    return NV12EQ_OK;
+}
+static int launch_nv12_bgr(nv12eq_ctx* ctx, bool to_bgr, const uint8_t* d_in, uint8_t* d_out, int n, size_t in_pitch, size_t out_pitch, int w,
+                           int h, int stride, int bgr_stride, cudaStream_t st) {
+    if (n == 0) return NV12EQ_OK;
+    if (n > 65535) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "at most 65535 frames per call");
+    Nv12BgrParams p{};
+    p.in = d_in; p.out = d_out; p.in_pitch = in_pitch; p.out_pitch = out_pitch; p.w = w; p.h = h; p.nv12_stride = stride; p.bgr_stride = bgr_stride;
+    const long long blocks = (long long)((w + 3) / 4) * (h / 2);
+    const int gx = (int)std::max<long long>(1, std::min<long long>((blocks + kColorThreads - 1) / kColorThreads, (long long)ctx->sm_count * 8));
+    if (to_bgr) nv12_to_bgr_kernel<<<dim3(gx, n), kColorThreads, 0, st>>>(p);
+    else bgr_to_nv12_kernel<<<dim3(gx, n), kColorThreads, 0, st>>>(p);
+    ctx->ctr.kernel_launches++;
+    CK(ctx, cudaGetLastError());
+    return NV12EQ_OK;
+}
+static int nv12_bgr_device(nv12eq_ctx* ctx, bool to_bgr, const uint8_t* d_in, uint8_t* d_out, int n_frames, size_t nv12_pitch, size_t bgr_pitch,
+                           int width, int height, int stride, int bgr_stride, void* cuda_stream) {
+    int rc = check_nv12_bgr(ctx, width, height, stride, bgr_stride);
+    if (rc) return rc;
+    if (!d_in || !d_out || n_frames < 0 ||
+        (n_frames > 1 && (nv12_pitch < nv12_frame_bytes(stride, height) || bgr_pitch < (size_t)bgr_stride * height)))
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    DeviceGuard guard(ctx->device);
+    rc = launch_nv12_bgr(ctx, to_bgr, d_in, d_out, n_frames, to_bgr ? nv12_pitch : bgr_pitch, to_bgr ? bgr_pitch : nv12_pitch, width, height, stride,
+                         bgr_stride, pick_stream(ctx, cuda_stream));
+    if (!rc) ctx->ctr.frames += (uint64_t)n_frames;
+    return rc;
+}
+static int nv12_bgr_host(nv12eq_ctx* ctx, bool to_bgr, const uint8_t* in, size_t in_size, uint8_t* out, size_t out_size, int width, int height,
+                         int stride, int bgr_stride) {
+    int rc = check_nv12_bgr(ctx, width, height, stride, bgr_stride);
+    if (rc) return rc;
+    if (!in || !out) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "null frame pointer");
+    const size_t nv12_need = nv12_frame_bytes(stride, height);
+    const size_t bgr_need = (size_t)bgr_stride * (height - 1) + 3 * (size_t)width;   // the buffer may end with the last pixel
+    const size_t in_need = to_bgr ? nv12_need : bgr_need, out_need = to_bgr ? bgr_need : nv12_need;
+    if (in_size < in_need || out_size < out_need)
+        return fail(ctx, NV12EQ_ERR_SHORT_BUFFER, "buffers %zu / %zu bytes < %zu / %zu bytes", in_size, out_size, in_need, out_need);
+    DeviceGuard guard(ctx->device);
+    Lane& L = ctx->lanes[0];
+    if ((rc = lane_wait(ctx, L))) return rc;
+    if ((rc = dev_reserve(ctx, L.d_in, in_need, false))) return rc;
+    if ((rc = dev_reserve(ctx, L.d_out, out_need, false))) return rc;
+    CK(ctx, cudaMemcpyAsync(L.d_in.p, in, in_need, cudaMemcpyHostToDevice, L.stream));
+    // rows of a strided output keep whatever the device buffer held between them: upload the caller's bytes first when there are gaps
+    const bool gaps = to_bgr ? (bgr_stride != 3 * width) : (stride != width);
+    if (gaps) CK(ctx, cudaMemcpyAsync(L.d_out.p, out, out_need, cudaMemcpyHostToDevice, L.stream));
+    rc = launch_nv12_bgr(ctx, to_bgr, reinterpret_cast<const uint8_t*>(L.d_in.p), reinterpret_cast<uint8_t*>(L.d_out.p), 1, in_need, out_need, width,
+                         height, stride, bgr_stride, L.stream);
+    if (rc) { cudaStreamSynchronize(L.stream); return rc; }
+    CK(ctx, cudaMemcpyAsync(out, L.d_out.p, out_need, cudaMemcpyDeviceToHost, L.stream));
+    CK(ctx, cudaStreamSynchronize(L.stream));
+    ctx->ctr.bytes_in += in_need; ctx->ctr.bytes_out += out_need; ctx->ctr.frames++;
+    return NV12EQ_OK;
+}
+int nv12eq_nv12_to_bgr(nv12eq_ctx* ctx, const uint8_t* nv12, size_t nv12_size, int width, int height, int stride, uint8_t* bgr, size_t bgr_size,
+                       int bgr_stride) {
+    return nv12_bgr_host(ctx, true, nv12, nv12_size, bgr, bgr_size, width, height, stride, bgr_stride);
+}
+int nv12eq_bgr_to_nv12(nv12eq_ctx* ctx, const uint8_t* bgr, size_t bgr_size, int width, int height, int bgr_stride, uint8_t* nv12, size_t nv12_size,
+                       int stride) {
+    return nv12_bgr_host(ctx, false, bgr, bgr_size, nv12, nv12_size, width, height, stride, bgr_stride);
+}
+int nv12eq_nv12_to_bgr_device(nv12eq_ctx* ctx, const uint8_t* d_nv12, uint8_t* d_bgr, int n_frames, size_t nv12_pitch, size_t bgr_pitch, int width,
+                              int height, int stride, int bgr_stride, void* cuda_stream) {
+    return nv12_bgr_device(ctx, true, d_nv12, d_bgr, n_frames, nv12_pitch, bgr_pitch, width, height, stride, bgr_stride, cuda_stream);
+}
+int nv12eq_bgr_to_nv12_device(nv12eq_ctx* ctx, const uint8_t* d_bgr, uint8_t* d_nv12, int n_frames, size_t bgr_pitch, size_t nv12_pitch, int width,
+                              int height, int bgr_stride, int stride, void* cuda_stream) {
+    return nv12_bgr_device(ctx, false, d_bgr, d_nv12, n_frames, nv12_pitch, bgr_pitch, width, height, stride, bgr_stride, cuda_stream);
+}
+
 // ---- ordered, back-pressured frame stream ---------------------------------------------------------------
 // FIFO ring of `depth` lanes.  push() takes the tail lane, pop() the head lane, so delivery order == push order by
 // construction; sequence numbers make drops visible to the consumer.

@@ -482,6 +482,52 @@ ORACLE_API int oracle_bgr2i420(const uint8_t* bgr, int stride, uint8_t* out, int
     return 0;
 }
 
+/* cv::cvtColor(nv12, COLOR_YUV2BGR_NV12): the display-side inverse of the NV12 path (the reference's
+ * pipelines hand NV12 to the encoder, its still-image tools convert back with cvtColor, singlecolor.cpp:66 / clahe1frame.cpp:102).
+ * OpenCV's YUV420sp2RGB: Q20 limited-range BT.601, one chroma pair per 2x2 block, saturating.  W and H even.
+ * nv12: Y rows at `stride`, UV rows at nv12 + stride * H. */
+ORACLE_API int oracle_nv12_to_bgr(const uint8_t* nv12, int stride, uint8_t* bgr, int bgr_stride, int W, int H) {
+    if (!nv12 || !bgr || W <= 0 || H <= 0 || (W & 1) || (H & 1) || stride < W || bgr_stride < 3 * W) return -1;
+    const uint8_t* uv = nv12 + (size_t)stride * H;
+    for (int r = 0; r < H; ++r) {
+        const uint8_t* yrow = nv12 + (size_t)r * stride;
+        const uint8_t* uvrow = uv + (size_t)(r / 2) * stride;
+        uint8_t* d = bgr + (size_t)r * bgr_stride;
+        for (int c = 0; c < W; ++c) {
+            const int u = (int)uvrow[c & ~1] - 128, v = (int)uvrow[(c & ~1) + 1] - 128;
+            const int y = (yrow[c] > 16 ? (int)yrow[c] - 16 : 0) * 1220542;
+            const int ruv = (1 << 19) + 1673527 * v;
+            const int guv = (1 << 19) - 852492 * v - 409993 * u;
+            const int buv = (1 << 19) + 2116026 * u;
+            const int B = (y + buv) >> 20, G = (y + guv) >> 20, R = (y + ruv) >> 20;
+            d[3 * c] = (uint8_t)(B < 0 ? 0 : B > 255 ? 255 : B);
+            d[3 * c + 1] = (uint8_t)(G < 0 ? 0 : G > 255 ? 255 : G);
+            d[3 * c + 2] = (uint8_t)(R < 0 ? 0 : R > 255 ? 255 : R);
+        }
+    }
+    return 0;
+}
+
+/* BGR -> NV12: the arithmetic of COLOR_BGR2YUV_I420 above with the two chroma planes interleaved (U first), i.e. the frame the
+ * NV12 operators take.  (OpenCV has no direct BGR -> NV12 code; the golden vectors are cv2's I420 output re-interleaved.) */
+ORACLE_API int oracle_bgr_to_nv12(const uint8_t* bgr, int bgr_stride, uint8_t* nv12, int stride, int W, int H) {
+    if (!bgr || !nv12 || W <= 0 || H <= 0 || (W & 1) || (H & 1) || stride < W || bgr_stride < 3 * W) return -1;
+    uint8_t* uv = nv12 + (size_t)stride * H;
+    for (int r = 0; r < H; ++r) {
+        const uint8_t* s = bgr + (size_t)r * bgr_stride;
+        for (int c = 0; c < W; ++c) {
+            const int B = s[3 * c], G = s[3 * c + 1], R = s[3 * c + 2];
+            nv12[(size_t)r * stride + c] = (uint8_t)((269484 * R + 528482 * G + 102760 * B + (16 << 20) + (1 << 19)) >> 20);
+            if (!(r & 1) && !(c & 1)) {
+                uint8_t* d = uv + (size_t)(r / 2) * stride + c;
+                d[0] = (uint8_t)((-155188 * R - 305135 * G + 460324 * B + (128 << 20) + (1 << 19)) >> 20);
+                d[1] = (uint8_t)((460324 * R - 385875 * G - 74448 * B + (128 << 20) + (1 << 19)) >> 20);
+            }
+        }
+    }
+    return 0;
+}
+
 /* Colour-path synthetic input (Appendix B): B,G,R planes = Y syntheses with seeds 3026/4026/5026. */
 ORACLE_API void oracle_synth_bgr(uint8_t* bgr, int stride, int W, int H, uint32_t frame) {
     uint8_t* plane = (uint8_t*)malloc((size_t)W * H);

@@ -88,6 +88,10 @@ def lib() -> ctypes.CDLL:
         L.oracle_clahe16.restype = c_int
         L.oracle_bgr2i420.argtypes = [_u8p, c_int, _u8p, c_int, c_int]
         L.oracle_bgr2i420.restype = c_int
+        L.oracle_nv12_to_bgr.argtypes = [_u8p, c_int, _u8p, c_int, c_int, c_int]
+        L.oracle_nv12_to_bgr.restype = c_int
+        L.oracle_bgr_to_nv12.argtypes = [_u8p, c_int, _u8p, c_int, c_int, c_int]
+        L.oracle_bgr_to_nv12.restype = c_int
         L.oracle_color_equalize.argtypes = [_u8p, _u8p, c_int, c_int, c_int, c_int, c_int, c_dbl, c_int, c_int]
         L.oracle_color_equalize.restype = c_int
         _lib = L
@@ -235,6 +239,27 @@ def c_bgr2i420(bgr: np.ndarray) -> np.ndarray:
     rc = lib().oracle_bgr2i420(_p(bgr), 3 * W, _p(out), W, H)
     if rc:
         raise ValueError("oracle_bgr2i420: width and height must be even")
+    return out
+
+
+def c_nv12_to_bgr(nv12: np.ndarray, W: int, H: int) -> np.ndarray:
+    """COLOR_YUV2BGR_NV12 of a flat NV12 frame (W*H*3/2 bytes): returns (H, W, 3) BGR."""
+    nv12 = np.ascontiguousarray(nv12).reshape(-1)
+    out = np.empty((H, W, 3), dtype=np.uint8)
+    rc = lib().oracle_nv12_to_bgr(_p(nv12), W, _p(out), 3 * W, W, H)
+    if rc:
+        raise ValueError("oracle_nv12_to_bgr: width and height must be even")
+    return out
+
+
+def c_bgr_to_nv12(bgr: np.ndarray) -> np.ndarray:
+    """BGR -> flat NV12 frame (COLOR_BGR2YUV_I420 arithmetic, chroma interleaved U first)."""
+    bgr = np.ascontiguousarray(bgr)
+    H, W, _ = bgr.shape
+    out = np.empty(W * H * 3 // 2, dtype=np.uint8)
+    rc = lib().oracle_bgr_to_nv12(_p(bgr), 3 * W, _p(out), W, W, H)
+    if rc:
+        raise ValueError("oracle_bgr_to_nv12: width and height must be even")
     return out
 
 
