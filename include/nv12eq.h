@@ -184,6 +184,18 @@ int nv12eq_equalize_apply_device(nv12eq_ctx* ctx, const uint8_t* d_y_in, uint8_t
                                  size_t plane_pitch, int width, int height, int stride, const uint32_t* d_hist,
                                  int64_t total_pixels, void* cuda_stream);
 
+/* Spatial split of ONE frame for CLAHE (optional): rank r holds tile rows [first_tile_row, first_tile_row +
+ * band_tiles_y) of the Y plane (the tile grid must divide the frame).  band_luts writes the band's band_tiles_y * tiles_x tile LUTs
+ * (256 bytes each, row-major) to d_luts.  The caller then exchanges one tile row of LUTs with each neighbour (NCCL send/recv of
+ * tiles_x * 256 bytes: sharding.SpatialSplitClahe) into a grid of (band_tiles_y + 2) * tiles_x tables -- row 0 = tile row
+ * first_tile_row - 1, row band_tiles_y + 1 = tile row first_tile_row + band_tiles_y; rows outside the frame are never read -- and
+ * band_apply interpolates the band with the weights of the whole frame.  d_y_band / d_out_band point at the band's first row. */
+int nv12eq_clahe_band_luts_device(nv12eq_ctx* ctx, const uint8_t* d_y_band, int width, int full_height, int stride, double clip_limit,
+                                  int tiles_x, int tiles_y, int first_tile_row, int band_tiles_y, uint8_t* d_luts, void* cuda_stream);
+int nv12eq_clahe_band_apply_device(nv12eq_ctx* ctx, const uint8_t* d_y_band, uint8_t* d_out_band, int width, int full_height, int stride,
+                                   int tiles_x, int tiles_y, int first_tile_row, int band_tiles_y, const uint8_t* d_luts_halo,
+                                   void* cuda_stream);
+
 /* ---- colour path: packed 8-bit BGR in, BGR out (stride in bytes, >= 3*width) --------------------------- */
 int nv12eq_color_equalize(nv12eq_ctx* ctx, const uint8_t* bgr_in, uint8_t* bgr_out, int width, int height, int stride,
                           int color_mode);

@@ -116,6 +116,8 @@ _SIGNATURES = {
     "nv12eq_sync": (_c_int, [_c_vp]),
     "nv12eq_hist_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "nv12eq_equalize_apply_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_vp, ctypes.c_int64, _c_vp]),
+    "nv12eq_clahe_band_luts_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, ctypes.c_double, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "nv12eq_clahe_band_apply_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "nv12eq_color_equalize": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int]),
     "nv12eq_color_equalize_batch": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_sz, _c_int, _c_int, _c_int, _c_int]),
     "nv12eq_color_clahe": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _c_int]),
@@ -407,6 +409,22 @@ class Context:
         self._check(self._lib.nv12eq_equalize_apply_device(self._h, _ptr(d_y_in), _ptr(d_y_out), n_planes, plane_pitch,
                                                            width, height, stride, _ptr(d_hist), int(total_pixels),
                                                            _stream_ptr(stream)))
+
+    def clahe_band_luts_device(self, d_y_band, width, full_height, clip_limit, tiles, first_tile_row, band_tiles_y, d_luts,
+                               stride=None, stream=None):
+        """Tile LUTs of tile rows [first_tile_row, first_tile_row + band_tiles_y) of one frame (spatial split, stage 1)."""
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_clahe_band_luts_device(self._h, _ptr(d_y_band), width, full_height, stride, float(clip_limit),
+                                                            int(tiles[0]), int(tiles[1]), first_tile_row, band_tiles_y, _ptr(d_luts),
+                                                            _stream_ptr(stream)))
+
+    def clahe_band_apply_device(self, d_y_band, d_out_band, width, full_height, tiles, first_tile_row, band_tiles_y, d_luts_halo,
+                                stride=None, stream=None):
+        """Interpolation of the band from its LUT grid with one halo tile row on either side (spatial split, stage 2)."""
+        stride = width if stride is None else stride
+        self._check(self._lib.nv12eq_clahe_band_apply_device(self._h, _ptr(d_y_band), _ptr(d_out_band), width, full_height, stride,
+                                                             int(tiles[0]), int(tiles[1]), first_tile_row, band_tiles_y,
+                                                             _ptr(d_luts_halo), _stream_ptr(stream)))
 
     # -- colour path ------------------------------------------------------------------------------------
     def color_equalize(self, bgr: np.ndarray, color_mode: int = COLOR_YUV, out=None) -> np.ndarray:

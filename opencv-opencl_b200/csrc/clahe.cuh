@@ -130,7 +130,14 @@ struct ClaheParams {
     unsigned long long uv_bytes, uv_chunk;  // flat
     int uv_rows_chunk;                      // strided
     int lag;
-    uint8_t* luts;         // [n_frames][tx*ty][256]
+    // Row-band mode (spatial split of one frame over GPUs, sharding.SpatialSplitClahe): the plane passed in is rows
+    // [y_origin, y_origin + h) of a taller frame.  tile_items = 0 runs the interpolation only, on a caller-supplied LUT grid that
+    // holds one halo row of tile LUTs above and below the band's own (y cells index into it); cells_off = 1 builds the LUTs only.
+    int tile_items;        // tile items per frame: tx * ty, or 0 (apply only)
+    int cells_off;         // 1: no cell and no uv items
+    int lut_tiles;         // LUT tables per frame in `luts`
+    int y_origin;          // frame row of the plane's first row (the y weights are those of the whole frame)
+    uint8_t* luts;         // [n_frames][lut_tiles][256]
     uint32_t* tiles_done;  // [n_frames] published tile LUTs per frame; self-cleaned
     uint32_t* ticket;      // [1] self-cleaned
     uint32_t* status;      // [1]
@@ -659,9 +666,9 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const __
         if (threadIdx.x == 0) atomicExch(p.status, 2u);
         return;
     }
-    const int T = p.tx * p.ty;
-    const int I = p.nxc * p.nyc;
-    const int U = p.uv_chunks;
+    const int T = p.tile_items;
+    const int I = p.cells_off ? 0 : p.nxc * p.nyc;
+    const int U = p.cells_off ? 0 : p.uv_chunks;
     const int per_slot = T + I + U;
     const uint32_t total_items = (uint32_t)(p.n_frames + p.lag) * (uint32_t)per_slot;
     const uint32_t lane4 = (uint32_t)(group * kHalfBytes + lane * 4);                        // hist column of this lane
@@ -799,7 +806,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const __
                 q.prefetch();  // the row sums and the LUT build hide the ticket round trip
                 group_sync(bar);
                 if (!(p.debug_skip & 8))
-                    clahe_tile_lut_block(hist256_row_sum(half, tid), p.clip_limit, p.lut_scale, p.luts + ((size_t)g * T + r) * 256, s_scratch,
+                    clahe_tile_lut_block(hist256_row_sum(half, tid), p.clip_limit, p.lut_scale, p.luts + ((size_t)g * p.lut_tiles + r) * 256, s_scratch,
                                          tid, bar);
                 publish = g;   // counted after the item's closing barrier, see publish_tile
             }
@@ -837,7 +844,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const __
                     // y weights of the cell's rows
                     for (int i = tid; i < ch; i += kCT) {
                         float ya, ya1;
-                        axis_weight(yc.x + i, p.inv_th, ya, ya1);
+                        axis_weight(p.y_origin + yc.x + i, p.inv_th, ya, ya1);
                         s_yw[i] = make_float2(ya1 * kYScale, ya * kYScale);
                     }
                     if (!q.current_ready()) {   // look-ahead did not see the tiles complete: poll (rare in steady state)
@@ -862,7 +869,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const __
                     if (!(p.debug_skip & 16))
                     // pack the four LUTs: row v = 16 replicas of {bf16 L11 | L21 << 16, bf16 L12 | L22 << 16}
                     {
-                        const uint8_t* L = p.luts + (size_t)f * T * 256;
+                        const uint8_t* L = p.luts + (size_t)f * p.lut_tiles * 256;
                         const int v = tid;
                         const uint32_t l11 = __ldcg(L + (size_t)(yc.z * p.tx + xc.z) * 256 + v);
                         const uint32_t l12 = __ldcg(L + (size_t)(yc.z * p.tx + xc.w) * 256 + v);

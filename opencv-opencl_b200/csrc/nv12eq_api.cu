@@ -478,8 +478,17 @@ bool encode_plane_map(CUtensorMap* m, const void* base, int w, int h, int n, siz
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Row-band mode of launch_clahe (spatial split of one frame over GPUs): the plane is tile rows [first_tile_row, first_tile_row + ty)
+// of a frame of full_h rows and full_ty tile rows (grid must divide the frame).  LutsOnly writes the band's ty * tx tables to
+// `luts`; ApplyOnly interpolates the band from `luts` = (ty + 2) * tx tables: tile rows first_tile_row - 1 .. first_tile_row + ty
+// (the rows outside the frame are never addressed: the y cells carry clamped tile rows).
+struct ClaheBand {
+    enum Mode { LutsOnly = 1, ApplyOnly = 2 } mode;
+    int full_h, full_ty, first_tile_row;
+    uint8_t* luts;
+};
 int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d_out, int n, size_t pitch, int w, int h,
-                 int stride, double clip, int tx, int ty, int uv_mode, cudaStream_t st) {
+                 int stride, double clip, int tx, int ty, int uv_mode, cudaStream_t st, const ClaheBand* band = nullptr) {
     if (n == 0) return NV12EQ_OK;
     if (tx < 1 || ty < 1 || (long long)tx * ty > (1 << 20)) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad tile grid %dx%d", tx, ty);
     int rc = ensure_attrs(ctx);
@@ -488,12 +497,25 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     if (rc) return rc;
     const ClaheGeom g = clahe_geometry(w, h, clip, tx, ty);
     const int T = tx * ty;
-    rc = dev_reserve(ctx, ws.luts, (size_t)n * T * 256, false);
-    if (rc) return rc;
-    if (ws.gw != w || ws.gh != h || ws.gtx != tx || ws.gty != ty || !ws.cells.p) {
+    if (!band) {
+        rc = dev_reserve(ctx, ws.luts, (size_t)n * T * 256, false);
+        if (rc) return rc;
+    }
+    if (band || ws.gw != w || ws.gh != h || ws.gtx != tx || ws.gty != ty || !ws.cells.p) {
         std::vector<int4> xc, yc;
         axis_cells(w, g.inv_tw, tx, 1024, 8, xc);
-        axis_cells(h, g.inv_th, ty, kMaxCellRows, 1, yc);
+        if (band && band->mode == ClaheBand::ApplyOnly) {
+            // the frame's y cells cut to the band's rows; tile rows re-based to the halo grid (row 0 = first_tile_row - 1)
+            std::vector<int4> all;
+            axis_cells(band->full_h, g.inv_th, band->full_ty, kMaxCellRows, 1, all);
+            const int Y0 = band->first_tile_row * g.th, Y1 = Y0 + h, base = band->first_tile_row - 1;
+            for (const int4& c : all) {
+                const int a = std::max(c.x, Y0), b = std::min(c.y, Y1);
+                if (a < b) yc.push_back(make_int4(a - Y0, b - Y0, c.z - base, c.w - base));
+            }
+        } else {
+            axis_cells(h, g.inv_th, ty, kMaxCellRows, 1, yc);
+        }
         rc = dev_reserve(ctx, ws.cells, (xc.size() + yc.size()) * sizeof(int4), false);
         if (rc) return rc;
         // stream-ordered after any kernel still reading the previous tables; the pageable source makes the call
@@ -501,7 +523,7 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
         CK(ctx, cudaMemcpyAsync(ws.cells.p, xc.data(), xc.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
         CK(ctx, cudaMemcpyAsync(reinterpret_cast<int4*>(ws.cells.p) + xc.size(), yc.data(), yc.size() * sizeof(int4),
                                 cudaMemcpyHostToDevice, st));
-        ws.gw = w; ws.gh = h; ws.gtx = tx; ws.gty = ty;
+        ws.gw = band ? -1 : w; ws.gh = h; ws.gtx = tx; ws.gty = ty;   // band tables are never reused
         ws.nxc = (int)xc.size(); ws.nyc = (int)yc.size();
         ws.h_cells = xc;
         ws.h_cells.insert(ws.h_cells.end(), yc.begin(), yc.end());
@@ -531,7 +553,13 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
         p.uv_rows_chunk = (h / 2 + U - 1) / U;
     }
     p.uv_chunks = U;
+    p.tile_items = T; p.lut_tiles = T;
     p.luts = reinterpret_cast<uint8_t*>(ws.luts.p);
+    if (band) {
+        p.luts = band->luts;
+        if (band->mode == ClaheBand::LutsOnly) p.cells_off = 1;
+        else { p.tile_items = 0; p.lut_tiles = tx * (ty + 2); p.y_origin = band->first_tile_row * g.th; }
+    }
     p.tiles_done = ws_counter(ws, 0);
     p.ticket = ws_ticket(ws);
     p.status = ws_status(ws);
@@ -567,7 +595,7 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
             if (ok) { p.tma_tiles = 1; p.tma_bw = bw; p.tma_nb = nb; p.tma_bh = bh; p.tma_bh_tail = tail; p.tma_nst = nst; }
         }
     }
-    const long long per_slot = (long long)T + (long long)p.nxc * p.nyc + U;
+    const long long per_slot = (long long)p.tile_items + (p.cells_off ? 0 : (long long)p.nxc * p.nyc + U);
     // CTAs per SM: four 64-register CTAs, or three with 80 registers (no rematerialisation in the blend loop).  Measured on
     // 4K frames with cool-downs between runs (tools/sweep.py --ctas 4,3,4,3 --cooldown 4): 8x8 grid (130 K-pixel tiles) 7.22 vs
     // 7.35 us per frame, 6x6 (230 K) 7.05 vs 7.04, 4x4 (518 K) 7.56 vs 7.48 -- the extra CTA wins until the tiles are so
@@ -1216,6 +1244,41 @@ int nv12eq_equalize_apply_device(nv12eq_ctx* ctx, const uint8_t* d_y_in, uint8_t
     DeviceGuard guard(ctx->device);
     return launch_equalize(ctx, ctx->dev_ws, d_y_in, d_y_out, n_planes, plane_pitch, width, height, stride, UV_SKIP,
                            pick_stream(ctx, cuda_stream), PH_APPLY | PH_EXTERNAL_HIST, const_cast<uint32_t*>(d_hist), (long long)total_pixels);
+}
+
+// ---- spatial split of one frame, CLAHE: band stages (the tile LUT halo exchange between them is the caller's NCCL send/recv) ----
+static int check_band(nv12eq_ctx* ctx, int width, int full_height, int stride, int tiles_x, int tiles_y, int first_tile_row, int band_tiles_y) {
+    if (!ctx) return NV12EQ_ERR_INVALID_ARGUMENT;
+    if (width <= 0 || full_height <= 0 || stride < width || tiles_x < 1 || tiles_y < 1 || first_tile_row < 0 || band_tiles_y < 1 ||
+        first_tile_row + band_tiles_y > tiles_y)
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad band arguments");
+    if (width % tiles_x != 0 || full_height % tiles_y != 0)
+        return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "the spatial split needs a tile grid that divides the frame (%dx%d tiles on %dx%d)", tiles_x, tiles_y,
+                    width, full_height);
+    if (width > ctx->max_w || full_height > ctx->max_h) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "frame exceeds the context maximum");
+    return NV12EQ_OK;
+}
+int nv12eq_clahe_band_luts_device(nv12eq_ctx* ctx, const uint8_t* d_y_band, int width, int full_height, int stride, double clip_limit, int tiles_x,
+                                  int tiles_y, int first_tile_row, int band_tiles_y, uint8_t* d_luts, void* cuda_stream) {
+    int rc = check_band(ctx, width, full_height, stride, tiles_x, tiles_y, first_tile_row, band_tiles_y);
+    if (rc) return rc;
+    if (!d_y_band || !d_luts || clip_limit < 0) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    DeviceGuard guard(ctx->device);
+    const int rows = full_height / tiles_y * band_tiles_y;
+    ClaheBand band{ClaheBand::LutsOnly, full_height, tiles_y, first_tile_row, d_luts};
+    return launch_clahe(ctx, ctx->dev_ws, d_y_band, nullptr, 1, 0, width, rows, stride, clip_limit, tiles_x, band_tiles_y, UV_SKIP,
+                        pick_stream(ctx, cuda_stream), &band);
+}
+int nv12eq_clahe_band_apply_device(nv12eq_ctx* ctx, const uint8_t* d_y_band, uint8_t* d_out_band, int width, int full_height, int stride, int tiles_x,
+                                   int tiles_y, int first_tile_row, int band_tiles_y, const uint8_t* d_luts_halo, void* cuda_stream) {
+    int rc = check_band(ctx, width, full_height, stride, tiles_x, tiles_y, first_tile_row, band_tiles_y);
+    if (rc) return rc;
+    if (!d_y_band || !d_out_band || !d_luts_halo) return fail(ctx, NV12EQ_ERR_INVALID_ARGUMENT, "bad arguments");
+    DeviceGuard guard(ctx->device);
+    const int rows = full_height / tiles_y * band_tiles_y;
+    ClaheBand band{ClaheBand::ApplyOnly, full_height, tiles_y, first_tile_row, const_cast<uint8_t*>(d_luts_halo)};
+    return launch_clahe(ctx, ctx->dev_ws, d_y_band, d_out_band, 1, 0, width, rows, stride, 0.0, tiles_x, band_tiles_y, UV_SKIP,
+                        pick_stream(ctx, cuda_stream), &band);
 }
 
 // ---- colour path ----------------------------------------------------------------------------------------

@@ -289,3 +289,70 @@ class SpatialSplitEqualizer:
                 self.ctx.equalize_apply_device(d_band_in, d_band_out, 1, self.width * rows, self.width, rows, hist,
                                                self.width * self.height, stream=st)
         return hist
+
+
+def tile_row_bands(tiles_y: int, world: int) -> List[Tuple[int, int]]:
+    """Spatial split of a CLAHE tile grid: [(first_tile_row, n_tile_rows)] per rank, contiguous, as even as possible."""
+    return [shard_range(tiles_y, r, world) for r in range(world)]
+
+
+def exchange_lut_halo(luts_halo, tiles_x: int, band_tiles_y: int, rank: int, world: int, group=None, has_rows=None):
+    """The one exchange of the spatially split CLAHE: every rank sends its first tile row of LUTs up and its last tile row down
+    and receives its neighbours' rows into the halo rows of `luts_halo` (a torch tensor [(band_tiles_y + 2) * tiles_x * 256] of
+    uint8 on the backend's device; rows 1 .. band_tiles_y are the rank's own).  tiles_x * 256 bytes per message (2 KB for an
+    8 x 8 grid): pure latency, like the 256-bin all-reduce of the equalizeHist split.  `has_rows[r]` says whether rank r owns any
+    tile row (ranks without rows neither send nor receive; their neighbours talk to the next rank that has rows)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or world <= 1 or band_tiles_y == 0:
+        return luts_halo
+    has = list(has_rows) if has_rows is not None else [True] * world
+    up = next((r for r in range(rank - 1, -1, -1) if has[r]), None)
+    down = next((r for r in range(rank + 1, world) if has[r]), None)
+    row = tiles_x * 256
+    first, last = luts_halo[row:2 * row], luts_halo[band_tiles_y * row:(band_tiles_y + 1) * row]
+    halo_top, halo_bot = luts_halo[0:row], luts_halo[(band_tiles_y + 1) * row:(band_tiles_y + 2) * row]
+    ops = []
+    if up is not None:
+        ops += [dist.P2POp(dist.isend, first, up, group), dist.P2POp(dist.irecv, halo_top, up, group)]
+    if down is not None:
+        ops += [dist.P2POp(dist.isend, last, down, group), dist.P2POp(dist.irecv, halo_bot, down, group)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return luts_halo
+
+
+class SpatialSplitClahe:
+    """CLAHE of ONE frame split by tile rows over the ranks of a process group (GPU path; needs libnv12eq + CUDA).
+
+    Every rank holds its band of the Y plane (whole tile rows; the tile grid must divide the frame) on its GPU.
+    `run` = nv12eq_clahe_band_luts_device on the band -> exchange of one tile row of LUTs with each neighbour (NCCL send/recv,
+    the only communication) -> nv12eq_clahe_band_apply_device.  Bit-exact with the single-GPU result: the tile LUTs depend on
+    the tile's pixels only, and the interpolation uses the weights of the whole frame."""
+
+    def __init__(self, ctx, width: int, height: int, clip_limit: float, tiles: Tuple[int, int], rank: int, world: int, group=None):
+        if width % tiles[0] or height % tiles[1]:
+            raise ValueError("the spatial split needs a tile grid that divides the frame")
+        self.ctx, self.width, self.height, self.clip, self.tiles = ctx, width, height, clip_limit, tiles
+        self.rank, self.world, self.group = rank, world, group
+        self.bands = tile_row_bands(tiles[1], world)
+        self.first_tile_row, self.band_tiles_y = self.bands[rank]
+        th = height // tiles[1]
+        self.band = (self.first_tile_row * th, self.band_tiles_y * th)   # (first row, rows) of this rank
+
+    def run(self, d_band_in, d_band_out, stream=None):
+        import torch
+        if stream is not None and not isinstance(stream, torch.cuda.Stream):
+            raise TypeError("SpatialSplitClahe.run: stream must be a torch.cuda.Stream or None (torch's current stream)")
+        st = stream if stream is not None else torch.cuda.current_stream(d_band_in.device)
+        tx, nb = self.tiles[0], self.band_tiles_y
+        with torch.cuda.stream(st):
+            luts = torch.zeros((nb + 2) * tx * 256, dtype=torch.uint8, device=d_band_in.device)
+            if nb > 0:
+                self.ctx.clahe_band_luts_device(d_band_in, self.width, self.height, self.clip, self.tiles, self.first_tile_row, nb,
+                                                luts[tx * 256:], stream=st)
+            exchange_lut_halo(luts, tx, nb, self.rank, self.world, self.group, [c > 0 for _, c in self.bands])
+            if nb > 0:
+                self.ctx.clahe_band_apply_device(d_band_in, d_band_out, self.width, self.height, self.tiles, self.first_tile_row, nb,
+                                                 luts, stream=st)
+        return luts

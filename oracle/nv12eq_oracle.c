@@ -242,6 +242,45 @@ ORACLE_API int oracle_clahe(const uint8_t* src, int sstride, uint8_t* dst, int d
 }
 
 
+/* Interpolation stage of oracle_clahe for rows [y_first, y_first + rows) of a W x H frame whose tile grid divides it, from a LUT
+ * grid with halo: `luts` holds tile rows first_tile_row - 1 .. (row-major, tx tables of 256 bytes per tile row); tile rows are
+ * clamped to the frame exactly as above, so the halo rows outside the frame are never read.  src / dst point at row y_first.
+ * This is the per-rank stage of the spatially split single-frame mode. */
+ORACLE_API int oracle_clahe_interp_band(const uint8_t* src, int sstride, uint8_t* dst, int dstride, int W, int H, int tx, int ty,
+                                        int y_first, int rows, const uint8_t* luts, int first_tile_row) {
+    if (!src || !dst || !luts || W <= 0 || H <= 0 || tx < 1 || ty < 1 || W % tx || H % ty || y_first < 0 || y_first + rows > H) return -1;
+    const int tw = W / tx, th = H / ty;
+    const float inv_tw = 1.0f / (float)tw, inv_th = 1.0f / (float)th;
+    for (int y = y_first; y < y_first + rows; ++y) {
+        float tyf = (float)y * inv_th - 0.5f;
+        int t1 = (int)floorf(tyf);
+        int t2 = t1 + 1;
+        float ya = tyf - (float)t1;
+        float ya1 = 1.0f - ya;
+        if (t1 < 0) t1 = 0;
+        if (t2 > ty - 1) t2 = ty - 1;
+        const uint8_t* plane1 = luts + (size_t)(t1 - (first_tile_row - 1)) * tx * 256;
+        const uint8_t* plane2 = luts + (size_t)(t2 - (first_tile_row - 1)) * tx * 256;
+        const uint8_t* s = src + (size_t)(y - y_first) * sstride;
+        uint8_t* d = dst + (size_t)(y - y_first) * dstride;
+        for (int x = 0; x < W; ++x) {
+            float txf = (float)x * inv_tw - 0.5f;
+            int x1 = (int)floorf(txf);
+            int x2 = x1 + 1;
+            float xa = txf - (float)x1;
+            float xa1 = 1.0f - xa;
+            if (x1 < 0) x1 = 0;
+            if (x2 > tx - 1) x2 = tx - 1;
+            int v = s[x];
+            float top = (float)plane1[x1 * 256 + v] * xa1 + (float)plane1[x2 * 256 + v] * xa;
+            float bot = (float)plane2[x1 * 256 + v] * xa1 + (float)plane2[x2 * 256 + v] * xa;
+            float res = top * ya1 + bot * ya;
+            d[x] = sat8(rne(res));
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------
  * CLAHE on CV_16UC1 (the P010 / 16-bit path OpenCV's CLAHE also accepts).
  * Same algorithm as A.2 with histSize = 65536, lutScale = 65535.f / tileArea, clipLimit = clip * tileArea / 65536

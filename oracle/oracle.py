@@ -88,6 +88,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_clahe16.restype = c_int
         L.oracle_bgr2i420.argtypes = [_u8p, c_int, _u8p, c_int, c_int]
         L.oracle_bgr2i420.restype = c_int
+        L.oracle_clahe_interp_band.argtypes = [_u8p, c_int, _u8p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _u8p, c_int]
+        L.oracle_clahe_interp_band.restype = c_int
         L.oracle_nv12_to_bgr.argtypes = [_u8p, c_int, _u8p, c_int, c_int, c_int]
         L.oracle_nv12_to_bgr.restype = c_int
         L.oracle_bgr_to_nv12.argtypes = [_u8p, c_int, _u8p, c_int, c_int, c_int]
@@ -183,6 +185,19 @@ def c_clahe_tile_luts(y: np.ndarray, clip=2.0, tx=8, ty=8) -> np.ndarray:
     luts = np.empty((ty * tx, 256), dtype=np.uint8)
     lib().oracle_clahe_tile_luts(_p(y), W, W, H, float(clip), tx, ty, _p(luts))
     return luts
+
+
+def c_clahe_interp_band(band: np.ndarray, H: int, tx: int, ty: int, y_first: int, luts_halo: np.ndarray, first_tile_row: int) -> np.ndarray:
+    """Interpolation of rows [y_first, y_first + band rows) of a W x H frame from a LUT grid with halo (tile rows
+    first_tile_row - 1 ..): the per-rank stage of the spatially split single-frame mode."""
+    band = np.ascontiguousarray(band)
+    rows, W = band.shape
+    luts_halo = np.ascontiguousarray(luts_halo).reshape(-1)
+    out = np.empty_like(band)
+    rc = lib().oracle_clahe_interp_band(_p(band), W, _p(out), W, W, H, tx, ty, y_first, rows, _p(luts_halo), first_tile_row)
+    if rc:
+        raise ValueError(f"oracle_clahe_interp_band rc={rc}")
+    return out
 
 
 def c_nv12_equalize_hist(nv12: np.ndarray, W, H, stride=None, uv_mode=UV_COPY, out=None) -> np.ndarray:

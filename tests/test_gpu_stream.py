@@ -206,6 +206,88 @@ def test_spatial_split_equalizer_two_gpus(nv):
     assert all(ok for _, ok, _ in res), res
 
 
+def test_spatial_split_clahe_stage_api_and_single_rank(nv, ctx, oracle):
+    """The band stages of the spatially split CLAHE on ONE GPU: two bands processed one after the other with the halo rows copied
+    by hand (what the NCCL send/recv does between ranks), and the world-size-1 form of SpatialSplitClahe."""
+    import torch
+    for (W, H, tiles, clip, splits) in ((1920, 1080, (8, 8), 2.0, [(0, 4), (4, 4)]), (3840, 2160, (8, 8), 3.0, [(0, 3), (3, 3), (6, 2)]),
+                                        (640, 480, (4, 6), 40.0, [(0, 1), (1, 5)])):
+        tx, ty = tiles
+        th = H // ty
+        y = oracle.c_synth_nv12(W, H, 2026, 1)[:W * H].reshape(H, W)
+        want = oracle.c_clahe(y, clip, tx, ty)
+        d_y = torch.from_numpy(y.copy()).cuda()
+        st = torch.cuda.current_stream()
+        all_luts = torch.zeros(ty * tx * 256, dtype=torch.uint8, device="cuda")
+        for first, nb in splits:   # stage 1 on every band
+            ctx.clahe_band_luts_device(d_y[first * th:], W, H, clip, tiles, first, nb, all_luts[first * tx * 256:], stream=st)
+        torch.cuda.synchronize()
+        assert np.array_equal(all_luts.cpu().numpy().reshape(-1, 256), oracle.c_clahe_tile_luts(y, clip, tx, ty))
+        d_out = torch.zeros_like(d_y)
+        for first, nb in splits:   # the exchange by hand, then stage 2
+            halo = torch.full(((nb + 2) * tx * 256,), 0xEE, dtype=torch.uint8, device="cuda")   # rows outside the frame stay garbage
+            lo, hi = max(first - 1, 0), min(first + nb + 1, ty)
+            halo[(lo - (first - 1)) * tx * 256:(hi - (first - 1)) * tx * 256] = all_luts[lo * tx * 256:hi * tx * 256]
+            ctx.clahe_band_apply_device(d_y[first * th:], d_out[first * th:], W, H, tiles, first, nb, halo, stream=st)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), want), (W, H)
+        one = nv.sharding.SpatialSplitClahe(ctx, W, H, clip, tiles, rank=0, world=1)
+        d_out.zero_()
+        one.run(d_y.reshape(-1), d_out.reshape(-1), stream=st)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), want)
+    with pytest.raises(nv.Nv12eqError):   # a grid that does not divide the frame is refused
+        ctx.clahe_band_luts_device(d_y, 1918, 1078, 2.0, (8, 8), 0, 4, all_luts)
+
+
+def _spatial_clahe_worker(rank, world, port, q):
+    """one rank of the 2-GPU spatially split CLAHE: own tile rows of one 4K luma plane, NCCL send/recv of one LUT row"""
+    import torch
+    import torch.distributed as dist
+    import opencv_opencl_b200 as nv
+    from oracle import oracle as O
+    try:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
+        W, H, tiles, clip = 3840, 2160, (8, 8), 2.0
+        y = O.c_synth_nv12(W, H, 2026, 3)[:W * H].reshape(H, W)
+        want = O.c_clahe(y, clip, *tiles)
+        ok = True
+        with nv.Context(rank, W, H, 1) as ctx:
+            sp = nv.sharding.SpatialSplitClahe(ctx, W, H, clip, tiles, rank, world)
+            first, rows = sp.band
+            d_in = torch.from_numpy(np.ascontiguousarray(y[first:first + rows]).reshape(-1)).cuda()
+            for stream in (None, torch.cuda.Stream()):
+                d_out = torch.zeros_like(d_in)
+                for _ in range(3):
+                    sp.run(d_in, d_out, stream=stream)
+                torch.cuda.synchronize()
+                ok = ok and np.array_equal(d_out.cpu().numpy().reshape(rows, W), want[first:first + rows])
+        dist.destroy_process_group()
+        q.put((rank, bool(ok), ""))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, False, repr(e)))
+
+
+def test_spatial_split_clahe_two_gpus(nv):
+    """SURVEY 8e optional mode for CLAHE with a real exchange: two ranks, two GPUs, one LUT-row send/recv per neighbour."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctxmp.Process(target=_spatial_clahe_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok, _ in res), res
+
+
 def test_cpp_example_runs_both_modes(nv):
     """The C++ example (reference worker loop over the C-ABI): worker pool + reorder buffer, and the nv12eq_stream form."""
     import os

@@ -181,8 +181,22 @@ def _worker(rank, world, port, result_dir):
         full = np.concatenate([b for _, b in sorted(bands, key=lambda t: t[0])])
         ok_split = bool(np.array_equal(full, O.c_equalize_hist(y)))
 
+        # (4) spatial split of ONE frame for CLAHE: band tile LUTs -> one LUT row to each neighbour (send/recv) -> band interpolation
+        tx, ty, clip = 4, 4, 2.0
+        th = H // ty
+        first_t, nb = sh.tile_row_bands(ty, world)[rank]
+        band = y[first_t * th:(first_t + nb) * th]
+        halo = torch.full(((nb + 2) * tx * 256,), 0xEE, dtype=torch.uint8)
+        halo[tx * 256:(nb + 1) * tx * 256] = torch.from_numpy(O.c_clahe_tile_luts(band, clip, tx, nb).reshape(-1))
+        sh.exchange_lut_halo(halo, tx, nb, rank, world)
+        out_band = O.c_clahe_interp_band(band, H, tx, ty, first_t * th, halo.numpy(), first_t)
+        bands = [None] * world
+        dist.all_gather_object(bands, (first_t, out_band))
+        full = np.concatenate([b for _, b in sorted(bands, key=lambda t: t[0])])
+        ok_clahe = bool(np.array_equal(full, O.c_clahe(y, clip, tx, ty)))
+
         with open(os.path.join(result_dir, f"rank{rank}.txt"), "w") as f:
-            f.write(f"{ok_batch} {ok_stream} {ok_hist} {ok_split}")
+            f.write(f"{ok_batch} {ok_stream} {ok_hist} {ok_split} {ok_clahe}")
     finally:
         dist.destroy_process_group()
 
@@ -192,4 +206,4 @@ def test_gloo_world2_frame_sharding_and_spatial_split(tmp_path):
     world, port = 2, _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
-        assert open(tmp_path / f"rank{r}.txt").read() == "True True True True", f"rank {r}"
+        assert open(tmp_path / f"rank{r}.txt").read() == "True True True True True", f"rank {r}"
