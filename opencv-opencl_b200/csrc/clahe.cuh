@@ -137,6 +137,10 @@ struct ClaheParams {
     int cells_off;         // 1: no cell and no uv items
     int lut_tiles;         // LUT tables per frame in `luts`
     int y_origin;          // frame row of the plane's first row (the y weights are those of the whole frame)
+    // interpolation weights, computed once per geometry on the host with the device's operation order (separately rounded
+    // multiply, subtract, floor, subtract): xw[x] = xa(x) * kXScale, yw[y] = {(1 - ya(y)) * kYScale, ya(y) * kYScale}
+    const float* xw;       // [w]
+    const float2* yw;      // [frame height]
     uint8_t* luts;         // [n_frames][lut_tiles][256]
     uint32_t* tiles_done;  // [n_frames] published tile LUTs per frame; self-cleaned
     uint32_t* ticket;      // [1] self-cleaned
@@ -588,15 +592,19 @@ struct CellRows {
     }
     // Everything that does not depend on the tile LUTs: x weights and the first D-1 iterations of the ring.  Called BEFORE
     // the dependency wait and the table build, so the pixel loads are in flight while the CTA waits for / packs the LUTs.
-    __device__ __forceinline__ void start(const uint8_t* sp, uint8_t* dp_, size_t rstep_, int nrows_, int xg, float inv_tw, int tid, int group,
+    __device__ __forceinline__ void start(const uint8_t* sp, uint8_t* dp_, size_t rstep_, int nrows_, const float* xwp, int tid, int group,
                                           uint32_t yw_off_, uint32_t yw_step_) {
         dp = dp_; rstep = rstep_; nrows = nrows_; ring0 = ring_base(tid, group); yw_off = yw_off_; yw_step = yw_step_;
+        if (nrows > 0) {   // xwp is 32-byte aligned (the group's first column is a multiple of 8) and inside the table
 #pragma unroll
-        for (int k = 0; k < G; k += 2) {
-            float a0, a1, b0, b1;
-            axis_weight(xg + k, inv_tw, a0, b0);
-            axis_weight(xg + k + 1, inv_tw, a1, b1);
-            xw[k / 2] = pack_f2(a0 * kXScale, a1 * kXScale);
+            for (int k = 0; k < G; k += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(xwp + k));
+                xw[k / 2] = pack_f2(v.x, v.y);
+                xw[k / 2 + 1] = pack_f2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < G / 2; ++k) xw[k] = 0ull;
         }
 #pragma unroll
         for (int j = 0; j < D - 1; ++j) {
@@ -842,11 +850,7 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const __
                 // started by then (CellRows::start), so pixel loads overlap the wait and the LUT loads
                 auto wait_and_build_table = [&]() -> bool {
                     // y weights of the cell's rows
-                    for (int i = tid; i < ch; i += kCT) {
-                        float ya, ya1;
-                        axis_weight(p.y_origin + yc.x + i, p.inv_th, ya, ya1);
-                        s_yw[i] = make_float2(ya1 * kYScale, ya * kYScale);
-                    }
+                    for (int i = tid; i < ch; i += kCT) s_yw[i] = __ldg(p.yw + p.y_origin + yc.x + i);
                     if (!q.current_ready()) {   // look-ahead did not see the tiles complete: poll (rare in steady state)
                         if (tid == 0) {
                             bool ok = true;
@@ -894,12 +898,12 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const __
                 bool ok;
                 if (fast16 && kUseG16) {
                     CellRows<16, kRows16, kRingBytesPerThread / (16 * kRows16)> cr;
-                    cr.start(sp, dp, rstep, nrows, xg, p.inv_tw, tid, group, yw_off, yw_step);
+                    cr.start(sp, dp, rstep, nrows, p.xw + xg, tid, group, yw_off, yw_step);
                     ok = wait_and_build_table();
                     if (ok) cr.run(q, lane8);
                 } else {
                     CellRows<8, 2, kRingBytesPerThread / 16> cr;
-                    cr.start(sp, dp, rstep, nrows, xg, p.inv_tw, tid, group, yw_off, yw_step);
+                    cr.start(sp, dp, rstep, nrows, p.xw + xg, tid, group, yw_off, yw_step);
                     ok = wait_and_build_table();
                     if (ok) cr.run(q, lane8);
                 }
@@ -911,10 +915,9 @@ __global__ void __launch_bounds__(kBlockThreads, MIN_CTAS) clahe_kernel(const __
                     for (long long i = tid; i < npix; i += kCT) {
                         const int ry = (int)(i / sw), rx = (int)(i - (long long)ry * sw);
                         const int x = xslow + rx, yy = yc.x + ry;
-                        float xa, xa1;
-                        axis_weight(x, p.inv_tw, xa, xa1);
+                        const float xa = __ldg(p.xw + x), xa1 = __fsub_rn(kXScale, xa);   // (1 - xa) * kXScale, exactly
                         const uint32_t v = src[(size_t)yy * p.stride + x];
-                        const float res = clahe_blend_res(lds_entry_rel((v << kRowShift) + lane8), xa * kXScale, xa1 * kXScale, lds_b64_rel(yw_base + (uint32_t)ry * 8u));
+                        const float res = clahe_blend_res(lds_entry_rel((v << kRowShift) + lane8), xa, xa1, lds_b64_rel(yw_base + (uint32_t)ry * 8u));
                         dst[(size_t)yy * p.stride + x] = (uint8_t)__float_as_uint(__fadd_rn(res, 12582912.0f));
                     }
                 }

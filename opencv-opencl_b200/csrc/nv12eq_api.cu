@@ -76,6 +76,7 @@ struct Workspace {
     // cached CLAHE geometry
     int gw = 0, gh = 0, gtx = 0, gty = 0, nxc = 0, nyc = 0;
     std::vector<int4> h_cells;   // host copy of the cell tables (x cells, then y cells)
+    DevBuf weights;              // CLAHE interpolation weights of the cached geometry: float xw[w], then float2 yw[frame height]
 };
 
 // Small pool of host threads for the chroma plane of host-buffer calls.  In passthrough mode the chroma bytes never
@@ -253,7 +254,7 @@ void dev_release(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; 
 void host_release(HostBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
 
 void ws_release(Workspace& w) {
-    dev_release(w.hist); dev_release(w.counters); dev_release(w.misc); dev_release(w.luts); dev_release(w.cells);
+    dev_release(w.hist); dev_release(w.counters); dev_release(w.misc); dev_release(w.luts); dev_release(w.cells); dev_release(w.weights);
     dev_release(w.luma); dev_release(w.hist16); dev_release(w.luts16); dev_release(w.cells16); dev_release(w.ormask16);
     w.frames_cap = 0; w.gw = w.gh = w.gtx = w.gty = 0;
 }
@@ -523,6 +524,28 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
         CK(ctx, cudaMemcpyAsync(ws.cells.p, xc.data(), xc.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
         CK(ctx, cudaMemcpyAsync(reinterpret_cast<int4*>(ws.cells.p) + xc.size(), yc.data(), yc.size() * sizeof(int4),
                                 cudaMemcpyHostToDevice, st));
+        // interpolation weights (same operation order as OpenCV / the oracle: every operation rounded separately, see the Makefile's
+        // -ffp-contract=off): x weights of the plane, y weights of the whole frame (a band indexes them from its first row)
+        {
+            const int fh = (band && band->mode == ClaheBand::ApplyOnly) ? band->full_h : h;
+            std::vector<float> wt((size_t)w + 2 * (size_t)fh);
+            auto frac = [](int pos, float inv, float& a, float& a1) {
+                volatile float f = (float)pos * inv;
+                volatile float g2 = f - 0.5f;
+                const float t1 = floorf(g2);
+                volatile float av = g2 - t1;
+                a = av;
+                volatile float bv = 1.0f - av;
+                a1 = bv;
+            };
+            for (int x = 0; x < w; ++x) { float a, a1; frac(x, g.inv_tw, a, a1); wt[x] = a * kXScale; }
+            for (int y = 0; y < fh; ++y) { float a, a1; frac(y, g.inv_th, a, a1); wt[(size_t)w + 2 * y] = a1 * kYScale; wt[(size_t)w + 2 * y + 1] = a * kYScale; }
+            const size_t xbytes = (((size_t)w * sizeof(float)) + 255) & ~(size_t)255;   // keeps the float2 table aligned
+            rc = dev_reserve(ctx, ws.weights, xbytes + 2 * (size_t)fh * sizeof(float), false);
+            if (rc) return rc;
+            CK(ctx, cudaMemcpyAsync(ws.weights.p, wt.data(), (size_t)w * sizeof(float), cudaMemcpyHostToDevice, st));
+            CK(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ws.weights.p) + xbytes, wt.data() + w, 2 * (size_t)fh * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
         ws.gw = band ? -1 : w; ws.gh = h; ws.gtx = tx; ws.gty = ty;   // band tables are never reused
         ws.nxc = (int)xc.size(); ws.nyc = (int)yc.size();
         ws.h_cells = xc;
@@ -538,6 +561,8 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     p.nxc = ws.nxc; p.nyc = ws.nyc;
     p.xcells = reinterpret_cast<const int4*>(ws.cells.p);
     p.ycells = p.xcells + ws.nxc;
+    p.xw = reinterpret_cast<const float*>(ws.weights.p);
+    p.yw = reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(ws.weights.p) + ((((size_t)w * sizeof(float)) + 255) & ~(size_t)255));
     p.cells_in_params = (ws.nxc <= kParamCells && ws.nyc <= kParamCells);
     if (p.cells_in_params) {
         std::copy(ws.h_cells.begin(), ws.h_cells.begin() + ws.nxc, p.xc_small);
@@ -617,7 +642,7 @@ int launch_clahe(nv12eq_ctx* ctx, Workspace& ws, const uint8_t* d_in, uint8_t* d
     if (items >= (1ll << 32)) return fail(ctx, NV12EQ_ERR_TOO_LARGE, "too many work items");
     // developer tool: NV12EQ_TRACE=<file> dumps per-item timestamps of this launch (synchronous, slow)
     DevBuf trace_buf;
-    const char* trace_path = getenv("NV12EQ_TRACE");
+    const char* trace_path = NV12EQ_ITEM_TRACE ? getenv("NV12EQ_TRACE") : nullptr;   // needs a build with -DNV12EQ_ITEM_TRACE=1
     if (trace_path) {
         rc = dev_reserve(ctx, trace_buf, (size_t)items * 4 * sizeof(unsigned long long), true);
         if (rc) return rc;

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Developer tool: run one CLAHE batch with NV12EQ_TRACE set and print a per-item-kind timing summary."""
+"""Developer tool: run one CLAHE batch with NV12EQ_TRACE set and print a per-item-kind timing summary.
+Needs a library built with the item trace compiled in:  make -C opencv-opencl_b200/csrc OUT=../libnv12eq_trace.so EXTRA=-DNV12EQ_ITEM_TRACE=1
+and NV12EQ_LIB pointing at it."""
 import os, sys, struct
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
