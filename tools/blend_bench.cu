@@ -132,20 +132,20 @@ __device__ __forceinline__ void round_pair(float a, float b, uint32_t& oa, uint3
     unpack_u2(add_f2(pack_f2(a, b), pack_f2(12582912.0f, 12582912.0f)), oa, ob);
 }
 
-template <int V>
-__global__ void __launch_bounds__(kThreads, 1) blend_kernel(unsigned long long* out, int iters, float inv_tw, float inv_th, uint32_t mulreg) {
+template <int V, int MAXT = kThreads>
+__global__ void __launch_bounds__(MAXT, 1) blend_kernel(unsigned long long* out, int iters, float inv_tw, float inv_th, uint32_t mulreg) {
     uint8_t* const rows = reinterpret_cast<uint8_t*>(smem_rows);
     const int tid = threadIdx.x, lane = tid & 31;
     using B = Blend<V>;
     if ((uint32_t)__cvta_generic_to_shared(rows) != 1024u) { if (tid == 0) out[2] = 99; return; }
     // tables and pixels
-    for (int v = tid; v < 256; v += kThreads)
+    for (int v = tid; v < 256; v += blockDim.x)
         B::fill_row(rows + v * kRowBytes, (v * 7 + 3) & 255, (v * 13 + 5) & 255, (255 - v), (v * 29 + 11) & 255);
-    for (int i = tid; i < 4 * kThreads * 4; i += kThreads) {
+    for (int i = tid; i < 4 * kThreads * 4; i += blockDim.x) {
         uint32_t h = i * 2654435761u; h ^= h >> 13; h *= 0x9e3779b1u; h ^= h >> 16;
         reinterpret_cast<uint32_t*>(rows + kRingOff)[i] = h;
     }
-    for (int i = tid; i < 64; i += kThreads) {
+    for (int i = tid; i < 64; i += blockDim.x) {
         const float f = (i + 100) * inv_th - 0.5f;
         const float ya = f - floorf(f), ya1 = 1.0f - ya;
         reinterpret_cast<float2*>(rows + kYwOff)[i] = B::yw(ya1, ya);
@@ -194,19 +194,19 @@ __global__ void __launch_bounds__(kThreads, 1) blend_kernel(unsigned long long* 
     if (tid == 0 && blockIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
 }
 
-template <int V>
+template <int V, int MAXT = kThreads>
 void run(const char* name, unsigned long long* d_out, int threads = kThreads) {
     const int iters = 4096;
-    cudaFuncSetAttribute(blend_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(blend_kernel<V, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     unsigned long long h[3] = {0, 0, 0};
     for (int k = 0; k < 2; ++k) {
         cudaMemset(d_out, 0, 24);
-        blend_kernel<V><<<148, threads, kSmem>>>(d_out, iters, 1.0f / 480.0f, 1.0f / 270.0f, 256u);
+        blend_kernel<V, MAXT><<<148, threads, kSmem>>>(d_out, iters, 1.0f / 480.0f, 1.0f / 270.0f, 256u);
     }
     cudaDeviceSynchronize();
     cudaMemcpy(h, d_out, 24, cudaMemcpyDeviceToHost);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, blend_kernel<V>);
+    cudaFuncGetAttributes(&fa, blend_kernel<V, MAXT>);
     // 8 warps per sub-partition, 16 pixels per lane and iteration
     printf("%-64s %6.2f cycles per 32 pixels per sub-partition, %3d regs, checksum %08x %s %s\n", name, (double)h[0] / ((double)iters * 16.0 * (threads / 128)),
            fa.numRegs, (unsigned)h[1], h[2] ? "SMEM BASE MISMATCH" : "", cudaGetErrorString(cudaGetLastError()));
@@ -230,5 +230,9 @@ int main() {
     run<1>("1 at 4 warps per sub-partition", d_out, 512);
     run<1>("1 at 2 warps per sub-partition", d_out, 256);
     run<7>("7 at 4 warps per sub-partition", d_out, 512);
+    run<7, 768>("7 at 6 warps per sub-partition, up to 80 registers", d_out, 768);
+    run<7, 512>("7 at 4 warps per sub-partition, up to 128 registers", d_out, 512);
+    run<6, 768>("6 at 6 warps per sub-partition, up to 80 registers", d_out, 768);
+    run<6, 512>("6 at 4 warps per sub-partition, up to 128 registers", d_out, 512);
     return 0;
 }
