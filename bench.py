@@ -301,6 +301,10 @@ def run_ours(args):
     from oracle import oracle as O     # checker only: spot checks and the cpu_baseline leg
 
     rank, world, local = dist_env()
+    if world > 1 and "NV12EQ_HOST_THREADS" not in os.environ:
+        # one process per GPU on ONE host: the library's default chroma pool (hardware threads / 4 per context) would put
+        # world * cores / 4 copy threads on the box; share the cores instead (2 threads per rank on a 32-vCPU box at N = 8)
+        os.environ["NV12EQ_HOST_THREADS"] = str(max(1, min(8, (os.cpu_count() or 8) // (2 * world))))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: nv12eq has no CPU fallback")
     torch.cuda.set_device(local)
