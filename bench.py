@@ -43,8 +43,8 @@ EXTRA_WORKLOADS = [("clahe_4k", "clahe", "4k", 256), ("clahe_1080p", "clahe", "1
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--op", default="equalize", choices=["equalize", "clahe", "color"])
     ap.add_argument("--size", default="4k", choices=sorted(SIZES))
