@@ -61,7 +61,7 @@ extern "C" {
 #endif
 
 #define NV12EQ_VERSION_MAJOR 0
-#define NV12EQ_VERSION_MINOR 1
+#define NV12EQ_VERSION_MINOR 2   /* 2: NV12 <-> BGR adapters, CLAHE band stages (spatial split) */
 
 typedef struct nv12eq_ctx nv12eq_ctx;
 
