@@ -50,7 +50,7 @@ def test_library_exports_every_declared_symbol(nv):
 def test_python_binding_table_matches_header(nv):
     assert sorted(nv._SIGNATURES) == header_functions()
     lib = nv.load_library()
-    assert lib.nv12eq_version() == 1
+    assert lib.nv12eq_version() == 2   # NV12EQ_VERSION_MAJOR * 100 + NV12EQ_VERSION_MINOR
     assert lib.nv12eq_status_string(nv.ERR_SHORT_BUFFER) == b"buffer too small for the frame"
 
 
