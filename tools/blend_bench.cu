@@ -46,8 +46,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 //  7: variant 1 with the x weights pinned
 template <int V>
 struct Blend {
-    static constexpr bool kByteTable = (V == 2 || V == 6);
-    static constexpr float kXScale = (V == 2 || V == 6 || V == 3) ? 1.2676506002282294e30f /* 2^100 */ : 1.0f;
+    static constexpr bool kByteTable = (V == 2 || V == 6 || V == 11 || V == 12 || V >= 20);
+    static constexpr float kXScale = (V == 2 || V == 6 || V == 3 || V == 11 || V == 12 || V >= 20) ? 1.2676506002282294e30f /* 2^100 */ : 1.0f;
     __device__ static __forceinline__ uint32_t lane_off(int lane) { return kByteTable ? lane * 4 : (V == 4 ? (lane & 7) * 16 : (lane & 15) * 8); }
     // table fill: row v
     __device__ static void fill_row(uint8_t* row, uint32_t l11, uint32_t l12, uint32_t l21, uint32_t l22) {
@@ -72,7 +72,7 @@ struct Blend {
     }
     // y weights as stored in shared memory
     __device__ static float2 yw(float ya1, float ya) {
-        if (V == 2 || V == 6) return make_float2(ya1 * 5.62949953421312e14f, ya * 5.62949953421312e14f);        // 2^49
+        if (V == 2 || V == 6 || V == 11 || V == 12 || V >= 20) return make_float2(ya1 * 5.62949953421312e14f, ya * 5.62949953421312e14f);        // 2^49
         if (V == 3) return make_float2(ya1 * 2199023255552.0f /* 2^41 */, ya * 5.62949953421312e14f /* 2^49 */);
         return make_float2(ya1, ya);
     }
@@ -125,6 +125,23 @@ struct Blend {
         return __fadd_rn(r0, r1);
     }
 };
+// Two table words (pixels P and Q of this lane) -> the four packed operand pairs, with two u8 tensor-core MMAs against constant
+// selection matrices: D[i][2t + c] = byte (2m + c) of the word lane 4i + t put in row i, so every lane gets bytes (0,1) resp. (2,3)
+// of its OWN two words as s32 = the subnormal floats L * 2^-149, already in adjacent registers.
+__device__ __forceinline__ void mma_unpack_pair(uint32_t eP, uint32_t eQ, uint32_t b01, uint32_t b23, uint64_t& AP, uint64_t& AQ, uint64_t& BP, uint64_t& BQ) {
+    uint32_t c0, c1, c2, c3, d0, d1, d2, d3;
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%7, %7, %7, %7};"
+                 : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3) : "r"(eP), "r"(eQ), "r"(b01), "r"(0u));
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%7, %7, %7, %7};"
+                 : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(eP), "r"(eQ), "r"(b23), "r"(0u));
+    AP = pack_u2(c0, c1); AQ = pack_u2(c2, c3); BP = pack_u2(d0, d1); BQ = pack_u2(d2, d3);
+}
+__device__ __forceinline__ float blend_from_pairs(uint64_t A, uint64_t B, float xa, float xa1, uint64_t ywp) {
+    const uint64_t S = add_f2_nofuse(mul_f2(A, pack_f2(xa1, xa1)), mul_f2(B, pack_f2(xa, xa)));
+    float r0, r1;
+    unpack_f2(mul_f2(S, ywp), r0, r1);
+    return __fadd_rn(r0, r1);
+}
 __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
@@ -161,6 +178,14 @@ __global__ void __launch_bounds__(MAXT, 1) blend_kernel(unsigned long long* out,
         if (V == 6 || V == 7) asm volatile("" : "+f"(xa1[k]));
     }
     const uint32_t lo = B::lane_off(lane);
+    uint32_t b01 = 0, b23 = 0;
+    {
+        const int n = lane >> 2, k0 = (lane & 3) * 4;
+        for (int j = 0; j < 4; ++j) {
+            if (k0 + j == 4 * (n >> 1) + (n & 1)) b01 |= 1u << (8 * j);
+            if (k0 + j == 4 * (n >> 1) + 2 + (n & 1)) b23 |= 1u << (8 * j);
+        }
+    }
     const uint32_t ring0 = kRingOff + tid * 16, out0 = kOutOff + tid * 16;
     uint32_t yw_off = kYwOff;
     uint32_t sum = 0;
@@ -175,6 +200,63 @@ __global__ void __launch_bounds__(MAXT, 1) blend_kernel(unsigned long long* out,
             uint32_t o[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
+                if (V >= 20) {   // ablations of the byte-table formulation (results differ from the reference by construction)
+                    constexpr int AB = V - 20;
+                    float g[4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        uint32_t e;
+                        if (AB & 1) e = (w[q] >> (8 * h)) * 0x01010101u + 0x00010203u;
+                        else e = lds32_rel(h == 0 ? row_off<0>(w[q], lo) : h == 1 ? row_off<1>(w[q], lo) : h == 2 ? row_off<2>(w[q], lo) : row_off<3>(w[q], lo));
+                        const uint64_t A = pack_u2(prmt(e, 0, 0x4440), prmt(e, 0, 0x4441)), Bv = pack_u2(prmt(e, 0, 0x4442), prmt(e, 0, 0x4443));
+                        const uint64_t S = add_f2_nofuse(mul_f2(A, pack_f2(xa1[4 * q + h], xa1[4 * q + h])), mul_f2(Bv, pack_f2(xa[4 * q + h], xa[4 * q + h])));
+                        float r0, r1;
+                        if (AB & 4) unpack_f2(S, r0, r1); else unpack_f2(mul_f2(S, ywp), r0, r1);
+                        g[h] = __fadd_rn(r0, r1);
+                    }
+                    if (AB & 2) {
+                        o[q] = __float_as_uint(g[0]) ^ __float_as_uint(g[1]) ^ __float_as_uint(g[2]) ^ __float_as_uint(g[3]);
+                    } else {
+                        uint32_t a, b, c, d;
+                        round_pair(g[0], g[1], a, b);
+                        round_pair(g[2], g[3], c, d);
+                        o[q] = pack_low_bytes(a, b, c, d);
+                    }
+                    continue;
+                }
+                if (V == 12) {   // one MMA per pixel pair for the (L11, L21) pairs, PRMT for the (L12, L22) pairs: tensor, alu and fma pipes share the work
+                    const uint32_t e[4] = {lds32_rel(row_off<0>(w[q], lo)), lds32_rel(row_off<1>(w[q], lo)), lds32_rel(row_off<2>(w[q], lo)), lds32_rel(row_off<3>(w[q], lo))};
+                    float g[4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t c0, c1, c2, c3;
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%7, %7, %7, %7};"
+                                     : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3) : "r"(e[2 * h]), "r"(e[2 * h + 1]), "r"(b01), "r"(0u));
+                        const uint64_t BP = pack_u2(prmt(e[2 * h], 0, 0x4442), prmt(e[2 * h], 0, 0x4443));
+                        const uint64_t BQ = pack_u2(prmt(e[2 * h + 1], 0, 0x4442), prmt(e[2 * h + 1], 0, 0x4443));
+                        g[2 * h] = blend_from_pairs(pack_u2(c0, c1), BP, xa[4 * q + 2 * h], xa1[4 * q + 2 * h], ywp);
+                        g[2 * h + 1] = blend_from_pairs(pack_u2(c2, c3), BQ, xa[4 * q + 2 * h + 1], xa1[4 * q + 2 * h + 1], ywp);
+                    }
+                    uint32_t a, b, c, d;
+                    round_pair(g[0], g[1], a, b);
+                    round_pair(g[2], g[3], c, d);
+                    o[q] = pack_low_bytes(a, b, c, d);
+                    continue;
+                }
+                if (V == 11) {
+                    const uint32_t e0 = lds32_rel(row_off<0>(w[q], lo)), e1 = lds32_rel(row_off<1>(w[q], lo));
+                    const uint32_t e2 = lds32_rel(row_off<2>(w[q], lo)), e3 = lds32_rel(row_off<3>(w[q], lo));
+                    uint64_t A0, A1, B0, B1, A2, A3, B2, B3;
+                    mma_unpack_pair(e0, e1, b01, b23, A0, A1, B0, B1);
+                    mma_unpack_pair(e2, e3, b01, b23, A2, A3, B2, B3);
+                    const float g0 = blend_from_pairs(A0, B0, xa[4 * q + 0], xa1[4 * q + 0], ywp), g1 = blend_from_pairs(A1, B1, xa[4 * q + 1], xa1[4 * q + 1], ywp);
+                    const float g2 = blend_from_pairs(A2, B2, xa[4 * q + 2], xa1[4 * q + 2], ywp), g3 = blend_from_pairs(A3, B3, xa[4 * q + 3], xa1[4 * q + 3], ywp);
+                    uint32_t a, b, c, d;
+                    round_pair(g0, g1, a, b);
+                    round_pair(g2, g3, c, d);
+                    o[q] = pack_low_bytes(a, b, c, d);
+                    continue;
+                }
                 const float f0 = B::template px<0>(w[q], lo, xa[4 * q + 0], xa1[4 * q + 0], ywp, mulreg);
                 const float f1 = B::template px<1>(w[q], lo, xa[4 * q + 1], xa1[4 * q + 1], ywp, mulreg);
                 const float f2 = B::template px<2>(w[q], lo, xa[4 * q + 2], xa1[4 * q + 2], ywp, mulreg);
@@ -223,6 +305,17 @@ int main() {
     run<3>("3: {L | L << 24} words, IMAD.WIDE unpack", d_out);
     run<4>("4: fp32 entries (LDS.128), no unpack", d_out);
     run<5>("5: bf16 pairs, PRMT unpack, scalar fp32", d_out);
+    run<11>("11: byte entries, unpack of a pixel pair with two u8 MMAs (IMMA.16816)", d_out);
+    run<20>("20: ablation base (= variant 6 written pixel by pixel)", d_out);
+    run<21>("21: no gather (entry computed from the pixel word)", d_out);
+    run<22>("22: no rounding / packing", d_out);
+    run<24>("24: no y stage", d_out);
+    run<23>("23: no gather, no rounding / packing", d_out);
+    run<27>("27: no gather, no rounding / packing, no y stage", d_out);
+    run<12>("12: byte entries, one u8 MMA per pixel pair for (L11, L21), PRMT for (L12, L22)", d_out);
+    run<12, 768>("12 at 6 warps per sub-partition, up to 80 registers", d_out, 768);
+    run<11, 768>("11 at 6 warps per sub-partition, up to 80 registers", d_out, 768);
+    run<11, 512>("11 at 4 warps per sub-partition, up to 128 registers", d_out, 512);
     run<8>("8: fp16 pairs, cvt.f32.f16 unpack (fma pipe)", d_out);
     run<10>("10: half fp16 cvt, half PRMT", d_out);
     run<9>("9: variant 1, every lane gathers row 0 (checksum differs)", d_out);
