@@ -92,6 +92,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+TMA_LIB_PATH = os.path.join(_HERE, "libnv12eq_tma.so")
+
+
+def build_variants(verbose: bool = False) -> str:
+    """Compile the measured-and-rejected TMA variant of the library (CLAHE tile rows staged by cp.async.bulk.tensor + mbarriers, colour
+    rounds as bulk copies) next to the shipped one; tests/test_variants.py loads it through NV12EQ_LIB in a subprocess."""
+    csrc = os.path.join(_HERE, "csrc")
+    out = subprocess.run(["make", "-C", csrc, "variants"], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout + out.stderr)
+    if out.returncode:
+        raise RuntimeError("building libnv12eq_tma.so failed (see output above)")
+    return TMA_LIB_PATH
+
+
 _SIGNATURES = {
     # name: (restype, argtypes)
     "nv12eq_version": (_c_int, []),
