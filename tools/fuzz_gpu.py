@@ -56,6 +56,19 @@ with nv.Context(0, 4096, 2304, 3) as ctx:
                                   pre.reshape(-1)[[i for k in range(n) for i in range(k * pitch + S * (H + H // 2), (k + 1) * pitch)]]):
                 fails += 1
                 print("GAP BYTES TOUCHED", op, dict(W=W, H=H, S=S, n=n, pitch=pitch), flush=True)
+        if cases % 5 == 0 and W % 2 == 0 and H % 2 == 0:   # colour path and adapters on the same geometry
+            bgr = O.c_synth_bgr(W, H, int(rng.integers(0, 50)))
+            mode = int(rng.integers(0, 2))
+            checks = [("color_equalize", ctx.color_equalize(bgr, mode), O.c_color_equalize(bgr, mode)),
+                      ("color_clahe", ctx.color_clahe(bgr, clip, (tx, ty), mode), O.c_color_equalize(bgr, mode, True, clip, tx, ty)),
+                      ("bgr_to_i420", ctx.bgr_to_i420(bgr), O.c_bgr2i420(bgr)),
+                      ("bgr_to_nv12", ctx.bgr_to_nv12(bgr), O.c_bgr_to_nv12(bgr))]
+            fr0 = np.ascontiguousarray(frames[:S * (H + H // 2)].reshape(-1, S)[:, :W]).reshape(-1)
+            checks.append(("nv12_to_bgr", ctx.nv12_to_bgr(fr0, W, H), O.c_nv12_to_bgr(fr0, W, H)))
+            for name, got_, want_ in checks:
+                if not np.array_equal(got_, want_):
+                    fails += 1
+                    print("MISMATCH", name, dict(W=W, H=H, mode=mode, clip=clip, tx=tx, ty=ty), flush=True)
         if cases % 7 == 0:   # host-buffer form of the same frame
             fr = frames[:S * (H + H // 2)].copy()
             got = ctx.clahe(fr, W, H, clip, (tx, ty), stride=S, uv_mode=uv, out=pre[:fr.size].copy())
